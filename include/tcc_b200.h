@@ -1,0 +1,128 @@
+/*
+ * tcc_b200.h -- C ABI of the B200-native `civector` UCC engine.
+ *
+ * Drop-in boundary for ONE path of TenCirChem (paths relative to the reference
+ * tree): the functions that `tencirchem/static/engine_ucc.py` dispatches to for
+ * engine="civector" --
+ *     GETVECTOR_MAP["civector"]        engine_ucc.py:33-39  -> evolve_civector.py:180  get_civector
+ *     ENERGY_AND_GRAD_MAP["civector"]  engine_ucc.py:110-116 -> evolve_civector.py:201 get_energy_and_grad_civector
+ *     APPLY_EXCITATION_MAP["civector"] engine_ucc.py:129-136 -> evolve_civector.py:311 apply_excitation_civector
+ * and the Hamiltonian action they call, hamiltonian.py:146-183 (`fci_func`).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every entry point returns an int status
+ *     (0 = ok, negative = error class below) and never throws;
+ *     tcc_last_error() returns the message of the last failure on this thread.
+ *   - `*_dev` pointers are device pointers on the plan's device, `*_host` are host
+ *     pointers.  A CI vector is `tcc_civector_size()` doubles, row-major [na, nb]
+ *     with the alpha string as the row (ci_utils.py:22-25); hcb: [1, nstr].
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Work is enqueued on it; calls that return host results synchronise it.
+ *   - a plan is not thread-safe; use one plan per host thread / stream.
+ */
+#ifndef TCC_B200_H
+#define TCC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tcc_plan tcc_plan;
+
+/* status codes; the Python host layer maps them back to the reference's exceptions */
+#define TCC_OK 0
+#define TCC_ERR_TOO_MANY_QUBITS (-1)   /* ValueError("Too many qubits ...")       ci_utils.py:19-20 */
+#define TCC_ERR_BAD_EXCITATION (-2)    /* ValueError("Excitation ... not supported") evolve_civector.py:92-93,
+                                          also spin-non-conserving tuples which the reference silently
+                                          mis-computes */
+#define TCC_ERR_BAD_ARGUMENT (-3)      /* shapes / null pointers / parameter ids  ucc.py:423-424 */
+#define TCC_ERR_NO_HAMILTONIAN (-4)    /* energy requested before tcc_set_hamiltonian */
+#define TCC_ERR_CUDA (-5)              /* CUDA runtime failure (message in tcc_last_error) */
+#define TCC_ERR_NO_DEVICE (-6)         /* no CUDA device: there is no CPU fallback */
+
+const char* tcc_last_error(void);
+const char* tcc_version(void);
+/* number of CUDA devices visible, or a negative status */
+int tcc_device_count(void);
+
+/* ---- plan: the cached excitation tables ------------------------------------------------
+ * Replaces get_ci_strings + get_operator_tensors (ci_utils.py:16-37, evolve_civector.py:113-150):
+ * instead of [M, N] tables it keeps, per distinct spin-string hop, a compact list of
+ * (source address, partner address, sign) -- SURVEY.md F3.
+ *   ex_ops_flat / ex_op_len : the excitation tuples, concatenated, and their lengths (2 or 4)
+ *   param_ids               : length n_ops, values >= 0 (engine_ucc.py:43-44 default is range)
+ *   device                  : CUDA device ordinal
+ */
+int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t* ex_ops_flat,
+                    const int32_t* ex_op_len, const int32_t* param_ids, int device, tcc_plan** out);
+void tcc_plan_destroy(tcc_plan* plan);
+
+int64_t tcc_civector_size(const tcc_plan* plan);  /* ucc.py:1282-1290 */
+int64_t tcc_num_strings(const tcc_plan* plan);    /* per-spin strings (hcb: all strings) */
+int tcc_num_ops(const tcc_plan* plan);
+int tcc_num_params(const tcc_plan* plan);         /* max(param_ids)+1, ucc.py:1266-1271 */
+/* bytes of device memory held by the plan's tables / workspaces */
+int64_t tcc_plan_device_bytes(const tcc_plan* plan);
+
+/* ---- introspection for bit-exact parity tests -------------------------------------------
+ * per-spin CI strings in address order (non-hcb: the beta strings of ci_utils.py:22; the full
+ * string of determinant (a, b) is (s[a] << n_qubits/2) + s[b]); hcb: ci_utils.py:31 */
+int tcc_ci_strings_spin(const tcc_plan* plan, uint64_t* out_host /* [num_strings] */);
+/* the [N] tables of evolve_civector.py:91-106 for excitation j, expanded on the host from the
+ * compact per-spin lists: partner address, G matrix element (fket_phase), diag of G^2 */
+int tcc_excitation_tables(const tcc_plan* plan, int j, uint64_t* perm_host, int8_t* phase_host,
+                          int8_t* f2_host);
+
+/* ---- Hamiltonian -------------------------------------------------------------------------
+ * Replaces get_h_fcifunc_from_integral (hamiltonian.py:146-155; pyscf absorb_h1e with fac 0.5)
+ * or, for an hcb plan, get_h_fcifunc_hcb_from_integral (hamiltonian.py:158-183).
+ * int1e [n, n], int2e [n, n, n, n] row-major doubles on the host, n = spatial orbitals. */
+int tcc_set_hamiltonian(tcc_plan* plan, const double* int1e_host, const double* int2e_host);
+/* sigma = H c   (apply_op, hamiltonian.py:240-252).  c and sigma must not alias. */
+int tcc_apply_h(tcc_plan* plan, const double* c_dev, double* sigma_dev, void* stream);
+
+/* ---- state preparation: get_civector, evolve_civector.py:180-198 ------------------------
+ * params_host [num_params]; init_dev NULL = HF determinant (ci_utils.py:83-87), else a CI vector
+ * on the device (copied, never modified); out_dev receives the evolved vector. */
+int tcc_civector(tcc_plan* plan, const double* params_host, const double* init_dev, double* out_dev,
+                 void* stream);
+
+/* ---- energy / energy and gradient: engine_ucc.py:79-89, evolve_civector.py:201-243 --------
+ * energy excludes e_core (added by the caller, ucc.py:655/:707).  grad_host [num_params] already
+ * holds 2 * sum over excitations sharing a parameter (evolve_civector.py:213-218). */
+int tcc_energy(tcc_plan* plan, const double* params_host, const double* init_dev, double* energy_host,
+               void* stream);
+int tcc_energy_and_grad(tcc_plan* plan, const double* params_host, const double* init_dev,
+                        double* energy_host, double* grad_host, void* stream);
+
+/* ---- G|c> for one excitation: apply_excitation_civector, evolve_civector.py:311-313 ------ */
+int tcc_apply_excitation(tcc_plan* plan, const double* c_dev, const int32_t* ex_op, int ex_op_len,
+                         double* out_dev, void* stream);
+
+/* ---- host-buffer conveniences (what a ctypes/cffi binding of the reference would call):
+ * inputs and outputs live in host memory; copies are part of the call. ---------------------- */
+int tcc_civector_host(tcc_plan* plan, const double* params_host, const double* init_host,
+                      double* out_host);
+int tcc_apply_h_host(tcc_plan* plan, const double* c_host, double* sigma_host);
+int tcc_energy_and_grad_host(tcc_plan* plan, const double* params_host, const double* init_host,
+                             double* energy_host, double* grad_host);
+int tcc_apply_excitation_host(tcc_plan* plan, const double* c_host, const int32_t* ex_op,
+                              int ex_op_len, double* out_host);
+
+/* ---- building blocks (used by the sharded multi-GPU driver and the benchmarks) ------------ */
+/* one UCC factor exp(theta G_j) applied in place to a device vector */
+int tcc_rotate(tcc_plan* plan, int j, double theta, double* c_dev, void* stream);
+/* reverse-sweep step for excitation j: ket,bra <- exp(-theta G_j); *grad_dev += <bra|G_j|ket> */
+int tcc_reverse_step(tcc_plan* plan, int j, double theta, double* ket_dev, double* bra_dev,
+                     double* grad_dev /* one double on the device */, void* stream);
+/* algorithmic CI-vector bytes one rotation of excitation j must move: 16 * |support_j| */
+int64_t tcc_op_support_bytes(const tcc_plan* plan, int j);
+/* kernel launches issued by this plan since creation (for bench.py's gpu_launches) */
+int64_t tcc_launch_count(const tcc_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCC_B200_H */

@@ -1,0 +1,298 @@
+"""Thin ansatz classes over the B200 engine with the call surface of the reference's
+``UCC / UCCSD / KUPCCGSD / PUCCD`` for THIS path only: ``from_integral``, ``energy``,
+``energy_and_grad``, ``civector``, ``apply_excitation``, ``kernel``, ``get_ex_ops`` and the size
+properties (tencirchem/static/ucc.py:52-125, :337-378, :440-479, :608-737, :1239-1290).
+
+The reference classes need PySCF for molecules, HF/MP2/CCSD references and RDMs; none of that is
+on the hot path, so these classes start from MO integrals (the reference's own ``from_integral``
+route, ucc.py:52-125) and leave the rest to TenCirChem itself -- when TenCirChem is installed, use
+its classes with ``engine="civector-b200"`` after ``tencirchem_b200.register()``.
+"""
+from __future__ import annotations
+
+from math import comb
+from time import time
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import engine_ucc
+from .ci_utils import get_ci_strings
+from .hamiltonian import get_h_from_integral
+
+
+def _uccsd_singles(no: int, nv: int):
+    """UCC.get_ex1_ops (ucc.py:889-936): alpha then beta copy of each i->a, one shared parameter."""
+    for i in range(no):
+        for a in range(nv):
+            yield ((2 * no + nv + a, no + nv + i), (no + a, i))
+
+
+def _uccsd_doubles(no: int, nv: int):
+    """UCC.get_ex2_ops (ucc.py:938-1031): yields groups of tuples that share one parameter."""
+    n = no + nv
+    occ_b, vir_b = (lambda i: i), (lambda a: no + a)
+    occ_a, vir_a = (lambda i: n + i), (lambda a: n + no + a)
+    for i in range(no):
+        for j in range(i):
+            for a in range(nv):
+                for b in range(a):
+                    yield ((vir_a(b), vir_a(a), occ_a(i), occ_a(j)), (vir_b(b), vir_b(a), occ_b(i), occ_b(j)))
+    for i in range(no):
+        for j in range(i + 1):
+            for a in range(nv):
+                for b in range(a + 1):
+                    if i == j and a == b:
+                        yield ((vir_b(a), vir_a(a), occ_a(i), occ_b(i)),)
+                        continue
+                    yield ((vir_b(b), vir_a(a), occ_a(i), occ_b(j)), (vir_a(b), vir_b(a), occ_b(i), occ_a(j)))
+                    if i != j and a != b:
+                        yield ((vir_b(a), vir_a(b), occ_a(i), occ_b(j)), (vir_a(a), vir_b(b), occ_b(i), occ_a(j)))
+
+
+def _flatten(groups, first_id=0):
+    ops, ids = [], []
+    pid = first_id
+    for group in groups:
+        for op in group:
+            ops.append(op)
+            ids.append(pid)
+        pid += 1
+    return ops, ids
+
+
+class UCC:
+    """Base class: integrals + an ordered excitation list (ucc.py:158-335 minus the PySCF parts)."""
+
+    def __init__(self, int1e, int2e, n_elec: int, e_core: float = 0.0, hcb: bool = False, engine: str = None,
+                 ex_ops: Sequence[Tuple] = None, param_ids: Sequence[int] = None, init_state=None):
+        self.int1e = np.asarray(int1e, dtype=np.float64)
+        self.int2e = np.asarray(int2e, dtype=np.float64)
+        self.n_elec = int(n_elec)
+        if self.n_elec % 2:
+            raise ValueError("UCC class does not support open shell system")  # ucc.py:207-208
+        self.e_core = float(e_core)
+        self.hcb = bool(hcb)
+        self._check_engine(engine)
+        self.engine = engine or engine_ucc.ENGINE_NAME
+        self.active = len(self.int1e)
+        self.n_qubits = self.active if self.hcb else 2 * self.active
+        self.hamiltonian = get_h_from_integral(self.int1e, self.int2e, self.n_elec, self.hcb, "fcifunc")
+        self.ex_ops = list(ex_ops) if ex_ops is not None else None
+        self._param_ids = list(param_ids) if param_ids is not None else None
+        self.init_guess = None
+        self.init_state = init_state
+        self.scipy_minimize_options = None
+        self.opt_res = None
+        self.params = None
+
+    @classmethod
+    def from_integral(cls, int1e, int2e, n_elec, e_core: float = 0, **kwargs):
+        """ucc.py:52-125."""
+        return cls(int1e, int2e, n_elec, e_core, **kwargs)
+
+    # ---- sizes (ucc.py:1239-1290) ----
+    @property
+    def no(self) -> int:
+        return self.n_elec // 2
+
+    @property
+    def nv(self) -> int:
+        return self.active - self.no
+
+    @property
+    def param_ids(self) -> List[int]:
+        if self._param_ids is None and self.ex_ops is not None:
+            return list(range(len(self.ex_ops)))
+        return self._param_ids
+
+    @param_ids.setter
+    def param_ids(self, v):
+        self._param_ids = v
+
+    @property
+    def n_params(self) -> int:
+        if not self.param_ids:
+            return 0
+        return max(self.param_ids) + 1
+
+    @property
+    def civector_size(self) -> int:
+        if not self.hcb:
+            return comb(self.n_qubits // 2, self.n_elec // 2) ** 2
+        return comb(self.n_qubits, self.n_elec // 2)
+
+    @property
+    def statevector_size(self) -> int:
+        return 1 << self.n_qubits
+
+    def get_ci_strings(self, strs2addr: bool = False):
+        """ucc.py:481-510."""
+        return get_ci_strings(self.n_qubits, self.n_elec, self.hcb, strs2addr=strs2addr)
+
+    # ---- argument checks (ucc.py:410-438) ----
+    def _check_engine(self, engine):
+        if engine not in (None, engine_ucc.ENGINE_NAME):
+            raise ValueError(f"Engine '{engine}' not supported")
+
+    def _sanity_check(self):
+        if self.ex_ops is None or self.param_ids is None:
+            raise ValueError("`ex_ops` or `param_ids` not defined")
+        if len(self.ex_ops) != len(self.param_ids):
+            raise ValueError(
+                f"Excitation operator size {len(self.ex_ops)} and parameter size {len(self.param_ids)} do not match"
+            )
+
+    def _check_params_argument(self, params, strict=True):
+        if params is None:
+            if self.params is not None:
+                params = self.params
+            elif strict:
+                raise ValueError("Run the `.kernel` method to determine the parameters first")
+            elif self.init_guess is not None:
+                params = self.init_guess
+            else:
+                params = np.zeros(self.n_params)
+        if len(params) != self.n_params:
+            raise ValueError(f"Incompatible parameter shape. {self.n_params} is desired. Got {len(params)}")
+        return np.asarray(params, dtype=np.float64)
+
+    # ---- the hot path ----
+    def civector(self, params=None, engine: str = None):
+        """ucc.py:440-479."""
+        self._sanity_check()
+        params = self._check_params_argument(params)
+        self._check_engine(engine)
+        return engine_ucc.get_civector(params, self.n_qubits, self.n_elec, self.ex_ops, self.param_ids, self.hcb, self.init_state)
+
+    def energy(self, params=None, engine: str = None) -> float:
+        """ucc.py:608-655."""
+        self._sanity_check()
+        params = self._check_params_argument(params)
+        self._check_engine(engine)
+        if params is self.params and self.opt_res is not None:
+            return self.opt_res["e"]
+        e = engine_ucc.get_energy(params, self.hamiltonian, self.n_qubits, self.n_elec, self.ex_ops, self.param_ids, self.hcb, self.init_state)
+        return float(e) + self.e_core
+
+    def energy_and_grad(self, params=None, engine: str = None):
+        """ucc.py:657-707."""
+        self._sanity_check()
+        params = self._check_params_argument(params)
+        self._check_engine(engine)
+        e, g = engine_ucc.get_energy_and_grad(
+            params, self.hamiltonian, self.n_qubits, self.n_elec, self.ex_ops, self.param_ids, self.hcb, self.init_state
+        )
+        return float(e + self.e_core), np.asarray(g)
+
+    def apply_excitation(self, state, ex_op: Tuple, engine: str = None):
+        """ucc.py:709-737."""
+        self._check_engine(engine)
+        return engine_ucc.apply_excitation(state, self.n_qubits, self.n_elec, ex_op, hcb=self.hcb)
+
+    def kernel(self) -> float:
+        """ucc.py:337-378: L-BFGS-B over ``energy_and_grad``."""
+        from scipy.optimize import minimize
+
+        self._sanity_check()
+        if self.init_guess is None:
+            self.init_guess = np.zeros(self.n_params)
+        if self.n_params == 0:
+            e = self.energy(np.zeros(0))
+            self.opt_res = {"e": e, "x": np.zeros(0), "success": True, "init_guess": self.init_guess}
+            self.params = self.opt_res["x"]
+            return e
+        t0 = time()
+        func = lambda x: tuple(np.asarray(v, dtype=np.float64) for v in self.energy_and_grad(x))
+        res = minimize(func, x0=np.asarray(self.init_guess, dtype=np.float64), jac=True, method="L-BFGS-B",
+                       options=self.scipy_minimize_options)
+        opt_res = dict(res)
+        opt_res["opt_time"] = time() - t0
+        opt_res["init_guess"] = self.init_guess
+        opt_res["e"] = float(res.fun)
+        self.opt_res = opt_res
+        self.params = res.x.copy()
+        return opt_res["e"]
+
+
+class UCCSD(UCC):
+    """uccsd.py:20-185 without amplitude screening (``pick_ex2=False, sort_ex2=False``)."""
+
+    def __init__(self, int1e, int2e, n_elec, e_core=0.0, **kwargs):
+        super().__init__(int1e, int2e, n_elec, e_core, hcb=False, **kwargs)
+        self.ex_ops, self.param_ids, self.init_guess = self.get_ex_ops()
+
+    def get_ex1_ops(self):
+        ops, ids = _flatten(_uccsd_singles(self.no, self.nv))
+        return ops, ids, [0.0] * (max(ids) + 1 if ids else 0)
+
+    def get_ex2_ops(self):
+        ops, ids = _flatten(_uccsd_doubles(self.no, self.nv))
+        return ops, ids, [0.0] * (max(ids) + 1 if ids else 0)
+
+    def get_ex_ops(self):
+        """uccsd.py:107-157."""
+        o1, p1, g1 = self.get_ex1_ops()
+        o2, p2, g2 = self.get_ex2_ops()
+        off = max(p1) + 1 if p1 else 0
+        return o1 + o2, p1 + [p + off for p in p2], g1 + g2
+
+
+class KUPCCGSD(UCC):
+    """kupccgsd.py:20-267: k layers of generalised paired doubles followed by generalised singles."""
+
+    def __init__(self, int1e, int2e, n_elec, e_core=0.0, k: int = 3, n_tries: int = 1, **kwargs):
+        super().__init__(int1e, int2e, n_elec, e_core, hcb=False, **kwargs)
+        self.k = k
+        self.n_tries = n_tries
+        self.ex_ops, self.param_ids, self.init_guess = self.get_ex_ops()
+
+    def get_ex1_ops(self):
+        n = self.no + self.nv
+        groups = (((n + a, n + i), (a, i)) for a in range(n) for i in range(a))
+        ops, ids = _flatten(groups)
+        return ops, ids, np.zeros(max(ids) + 1 if ids else 0)
+
+    def get_ex2_ops(self):
+        n = self.no + self.nv
+        groups = (((a, n + a, n + i, i),) for a in range(n) for i in range(a))
+        ops, ids = _flatten(groups)
+        return ops, ids, np.zeros(max(ids) + 1 if ids else 0)
+
+    def get_ex_ops(self):
+        """kupccgsd.py:127-177."""
+        o1, p1, _ = self.get_ex1_ops()
+        o2, p2, _ = self.get_ex2_ops()
+        ops, ids, nxt = [], [], 0
+        for _ in range(self.k):
+            for block_ops, block_ids in ((o2, p2), (o1, p1)):
+                ops += block_ops
+                ids += [i + nxt for i in block_ids]
+                nxt = ids[-1] + 1 if ids else 0
+        return ops, ids, np.random.rand(max(ids) + 1 if ids else 0) - 0.5
+
+    def kernel(self):
+        """kupccgsd.py:98-125: best of ``n_tries`` random starts."""
+        best = None
+        for _ in range(self.n_tries):
+            self.init_guess = np.random.rand(self.n_params) - 0.5
+            super().kernel()
+            if best is None or self.opt_res["e"] < best["e"]:
+                best = self.opt_res
+        self.opt_res = best
+        self.params = best["x"].copy()
+        self.init_guess = best["init_guess"]
+        return float(best["e"])
+
+
+class PUCCD(UCC):
+    """puccd.py:20-236: paired doubles on the hard-core-boson representation."""
+
+    def __init__(self, int1e, int2e, n_elec, e_core=0.0, **kwargs):
+        super().__init__(int1e, int2e, n_elec, e_core, hcb=True, **kwargs)
+        self.ex_ops, self.param_ids, self.init_guess = self.get_ex_ops()
+
+    def get_ex_ops(self):
+        """puccd.py:101-146."""
+        ops = [(self.no + a, i) for i in range(self.no) for a in range(self.nv - 1, -1, -1)]
+        return ops, list(range(len(ops))), [0.0] * len(ops)

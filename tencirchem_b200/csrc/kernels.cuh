@@ -1,0 +1,48 @@
+// sm_100a kernels of the civector engine (declarations of the host launchers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace tcc {
+
+struct Link;
+
+// One spin side of an excitation as the kernels see it: a list of (src, dst|sign<<31) string
+// addresses, or the identity (src == nullptr) over `len` strings.
+struct SideList {
+    const uint32_t* src;
+    const uint32_t* dst;
+    int len;
+};
+
+// c'_I = cos c_I + sin p c_J ; c'_J = cos c_J - sin p c_I over all pairs (I=(a,b), J=(a',b')) of the op
+void launch_rotate(double* c, int64_t nb, SideList rows, SideList cols, double cs, double sn_s0,
+                   cudaStream_t st);
+// same on ket and bra with -theta, plus *grad_out = sum p0 (bra_I ket_J - bra_J ket_I) (deterministic)
+void launch_reverse(double* ket, double* bra, int64_t nb, SideList rows, SideList cols, double cs,
+                    double sn_s0, double s0, double* partials, unsigned* ticket, double* grad_out,
+                    cudaStream_t st);
+// out = G c (out pre-zeroed)
+void launch_apply_g(const double* c, double* out, int64_t nb, SideList rows, SideList cols, double s0,
+                    cudaStream_t st);
+int reverse_partials_capacity();
+
+void launch_set_unit(double* c, int64_t n, cudaStream_t st);
+// deterministic dot product: out[0] = sum x*y
+void launch_dot(const double* x, const double* y, int64_t n, double* partials, unsigned* ticket,
+                double* out, cudaStream_t st);
+void launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, bool accumulate,
+                      cudaStream_t st);
+// out[r, :] (+)= sum_j val[r, j] * in[col[r, j], :]   (ELL rows, dense row vectors of length ncols)
+void launch_spmm_rows(const double* in, double* out, int64_t nrows, int64_t ncols, const uint32_t* ell_col,
+                      const double* ell_val, int width, bool accumulate, cudaStream_t st);
+// sigma(a', b') += sum_{pq,rs} W[pq,rs] <a'|E_pq|a><b'|E_rs|b> c(a,b)  (opposite-spin part, DMMA)
+void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, const Link* links, int ml,
+                     const double* w, int n, int n2p, cudaStream_t st);
+// hard-core-boson sigma (hamiltonian.py:158-183)
+void launch_sigma_hcb(const double* c, double* sigma, int64_t nstr, const uint32_t* strings, int n, int k,
+                      const double* diag1, const double* hop, const double* diag2, const int64_t* binom,
+                      int binom_ld, cudaStream_t st);
+
+}  // namespace tcc

@@ -1,0 +1,216 @@
+"""Python handle of a ``tcc_plan`` (include/tcc_b200.h): the cached excitation tables of one ansatz.
+
+Plays the role of the reference's ``CI_OPERATOR_BATCH_CACHE`` entry
+(tencirchem/static/evolve_civector.py:109-150) but holds compact per-spin hop lists on the GPU
+instead of ``[M, N]`` tables.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _dptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Plan:
+    def __init__(self, n_qubits: int, n_elec: int, ex_ops: Sequence[Sequence[int]], param_ids=None,
+                 hcb: bool = False, device: Optional[int] = 0):
+        """``device=None`` builds a host-only plan (strings / table introspection, no compute)."""
+        self.lib = _lib.load()
+        self.n_qubits, self.n_elec, self.hcb = int(n_qubits), int(n_elec), bool(hcb)
+        self.ex_ops = tuple(tuple(int(i) for i in op) for op in ex_ops)
+        if param_ids is None:  # engine_ucc.py:43-44
+            param_ids = range(len(self.ex_ops))
+        self.param_ids = tuple(int(i) for i in param_ids)
+        if len(self.param_ids) != len(self.ex_ops):
+            raise ValueError("param_ids and ex_ops have different lengths")
+        flat = np.asarray([i for op in self.ex_ops for i in op], dtype=np.int32)
+        lens = np.asarray([len(op) for op in self.ex_ops], dtype=np.int32)
+        pids = np.asarray(self.param_ids, dtype=np.int32)
+        handle = C.c_void_p()
+        ip = C.POINTER(C.c_int32)
+        _lib.check(
+            self.lib.tcc_plan_create(
+                self.n_qubits, self.n_elec, int(self.hcb), len(self.ex_ops),
+                flat.ctypes.data_as(ip), lens.ctypes.data_as(ip), pids.ctypes.data_as(ip),
+                -1 if device is None else int(device), C.byref(handle),
+            )
+        )
+        self.handle = handle
+        self.device = device
+        self.size = int(self.lib.tcc_civector_size(handle))
+        self.n_strings = int(self.lib.tcc_num_strings(handle))
+        self.n_params = int(self.lib.tcc_num_params(handle))
+        self.n_ops = len(self.ex_ops)
+        self._h_token = None
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.tcc_plan_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # ---- introspection (host) ----
+    def ci_strings_spin(self) -> np.ndarray:
+        out = np.zeros(self.n_strings, dtype=np.uint64)
+        _lib.check(self.lib.tcc_ci_strings_spin(self.handle, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def excitation_tables(self, j: int):
+        perm = np.zeros(self.size, dtype=np.uint64)
+        phase = np.zeros(self.size, dtype=np.int8)
+        f2 = np.zeros(self.size, dtype=np.int8)
+        _lib.check(
+            self.lib.tcc_excitation_tables(
+                self.handle, int(j), perm.ctypes.data_as(C.POINTER(C.c_uint64)),
+                phase.ctypes.data_as(C.POINTER(C.c_int8)), f2.ctypes.data_as(C.POINTER(C.c_int8)),
+            )
+        )
+        return perm, phase, f2
+
+    def op_support_bytes(self, j: int) -> int:
+        return int(self.lib.tcc_op_support_bytes(self.handle, int(j)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.tcc_launch_count(self.handle))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.tcc_plan_device_bytes(self.handle))
+
+    # ---- Hamiltonian ----
+    def set_hamiltonian(self, int1e, int2e, token=None):
+        n = self.n_qubits if self.hcb else self.n_qubits // 2
+        int1e, int2e = _f64(int1e), _f64(int2e)
+        if int1e.shape != (n, n):
+            raise ValueError(f"Invalid one-boby integral array shape: {int1e.shape}")  # hamiltonian.py:53-54
+        if int2e.shape != (n, n, n, n):
+            raise ValueError(f"Invalid two-boby integral array shape: {int2e.shape}")
+        _lib.check(self.lib.tcc_set_hamiltonian(self.handle, _dptr(int1e), _dptr(int2e)))
+        self._h_token = token if token is not None else object()
+
+    def _check_params(self, params) -> np.ndarray:
+        params = _f64(params).reshape(-1)
+        if len(params) < self.n_params:
+            raise ValueError(f"Incompatible parameter shape. {self.n_params} is desired. Got {len(params)}")  # ucc.py:423-424
+        return params
+
+    def _check_state(self, state, name="init_state") -> Optional[np.ndarray]:
+        if state is None:
+            return None
+        state = _f64(state).reshape(-1)
+        if len(state) != self.size:
+            raise ValueError(f"{name} has {len(state)} elements, the CI vector has {self.size}")
+        return state
+
+    # ---- host-buffer calls ----
+    def civector(self, params, init_state=None) -> np.ndarray:
+        params = self._check_params(params)
+        init = self._check_state(init_state)
+        out = np.empty(self.size, dtype=np.float64)
+        _lib.check(self.lib.tcc_civector_host(self.handle, _dptr(params), _dptr(init), _dptr(out)))
+        return out
+
+    def apply_h(self, civector) -> np.ndarray:
+        c = self._check_state(civector, "civector")
+        out = np.empty(self.size, dtype=np.float64)
+        _lib.check(self.lib.tcc_apply_h_host(self.handle, _dptr(c), _dptr(out)))
+        return out
+
+    def energy(self, params, init_state=None) -> float:
+        params = self._check_params(params)
+        init = self._check_state(init_state)
+        e = C.c_double(0.0)
+        _lib.check(self.lib.tcc_energy_and_grad_host(self.handle, _dptr(params), _dptr(init), C.byref(e), None))
+        return float(e.value)
+
+    def energy_and_grad(self, params, init_state=None):
+        params = self._check_params(params)
+        init = self._check_state(init_state)
+        e = C.c_double(0.0)
+        grad = np.zeros(max(self.n_params, 1), dtype=np.float64)
+        _lib.check(self.lib.tcc_energy_and_grad_host(self.handle, _dptr(params), _dptr(init), C.byref(e), _dptr(grad)))
+        g = np.zeros(params.shape)
+        g[: self.n_params] = grad[: self.n_params]
+        return float(e.value), g
+
+    def apply_excitation(self, civector, ex_op) -> np.ndarray:
+        c = self._check_state(civector, "civector")
+        op = np.asarray(ex_op, dtype=np.int32)
+        out = np.empty(self.size, dtype=np.float64)
+        _lib.check(
+            self.lib.tcc_apply_excitation_host(
+                self.handle, _dptr(c), op.ctypes.data_as(C.POINTER(C.c_int32)), len(op), _dptr(out)
+            )
+        )
+        return out
+
+    # ---- device-pointer calls (torch tensors own the memory) ----
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    @staticmethod
+    def _stream():
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _check_dev(self, t, name):
+        import torch
+
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous() or t.numel() != self.size:
+            raise ValueError(f"{name} must be a contiguous float64 CUDA tensor with {self.size} elements")
+
+    def civector_dev(self, params, out, init=None):
+        params = self._check_params(params)
+        self._check_dev(out, "out")
+        if init is not None:
+            self._check_dev(init, "init")
+        _lib.check(self.lib.tcc_civector(self.handle, _dptr(params), self._ptr(init), self._ptr(out), self._stream()))
+        return out
+
+    def apply_h_dev(self, c, sigma):
+        self._check_dev(c, "c")
+        self._check_dev(sigma, "sigma")
+        _lib.check(self.lib.tcc_apply_h(self.handle, self._ptr(c), self._ptr(sigma), self._stream()))
+        return sigma
+
+    def energy_and_grad_dev(self, params, init=None):
+        """Vectors stay in the plan's own device buffers; only (E, grad) come back."""
+        params = self._check_params(params)
+        if init is not None:
+            self._check_dev(init, "init")
+        e = C.c_double(0.0)
+        grad = np.zeros(max(self.n_params, 1), dtype=np.float64)
+        _lib.check(
+            self.lib.tcc_energy_and_grad(self.handle, _dptr(params), self._ptr(init), C.byref(e), _dptr(grad), self._stream())
+        )
+        return float(e.value), grad[: self.n_params].copy()
+
+    def rotate_dev(self, j, theta, c):
+        self._check_dev(c, "c")
+        _lib.check(self.lib.tcc_rotate(self.handle, int(j), float(theta), self._ptr(c), self._stream()))
+
+    def reverse_step_dev(self, j, theta, ket, bra, grad_slot):
+        self._check_dev(ket, "ket")
+        self._check_dev(bra, "bra")
+        _lib.check(
+            self.lib.tcc_reverse_step(
+                self.handle, int(j), float(theta), self._ptr(ket), self._ptr(bra), C.c_void_p(grad_slot.data_ptr()), self._stream()
+            )
+        )

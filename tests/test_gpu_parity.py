@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs, against the committed golden fixtures and the reference's published values, plus
+size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star): strings / index maps / signs bit-exact (tests/test_host_cpu.py);
+energies within 1e-10 Ha; gradients within 1e-8 Ha/rad; CI amplitudes within 1e-12.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bruteforce as bf
+from oracle import civector_numpy as O
+from oracle import pools
+from tencirchem_b200 import KUPCCGSD, PUCCD, UCC, UCCSD, engine_ucc
+from tencirchem_b200.evolve_civector import clear_cache
+from tencirchem_b200.hamiltonian import get_h_from_integral, random_integral
+from tencirchem_b200.plan import Plan
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "published_kat.json")))
+GOLD = np.load(os.path.join(HERE, "golden", "oracle_vectors.npz"))
+
+E_TOL = 1e-10
+G_TOL = 1e-8
+C_TOL = 1e-12
+
+
+def _params(n, seed=2077):
+    np.random.seed(seed)
+    return np.random.rand(n) - 0.5
+
+
+def test_native_library_is_what_runs():
+    import ctypes
+
+    from tencirchem_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.tcc_device_count() >= 1
+    assert isinstance(lib, ctypes.CDLL)
+    maps = open(f"/proc/{os.getpid()}/maps").read()
+    assert "libtcc_b200.so" in maps
+
+
+def test_h2_published_values():
+    k = KAT["h2_sto3g"]
+    int1e = np.diag([k["h00"], k["h11"]])
+    int2e = np.zeros((2, 2, 2, 2))
+    int2e[0, 0, 0, 0] = k["J00"]
+    int2e[1, 1, 1, 1] = k["J11"]
+    int2e[0, 0, 1, 1] = int2e[1, 1, 0, 0] = k["J01"]
+    for idx in [(0, 1, 0, 1), (0, 1, 1, 0), (1, 0, 0, 1), (1, 0, 1, 0)]:
+        int2e[idx] = k["K01"]
+    ucc = UCCSD.from_integral(int1e, int2e, 2, k["e_nuc"])
+    assert [list(o) for o in ucc.ex_ops] == k["ex_ops"] and ucc.param_ids == k["param_ids"]
+    np.testing.assert_array_equal(ucc.civector([0, 0]), [1.0, 0.0, 0.0, 0.0])  # ucc.py:466-467 doctest
+    assert round(ucc.energy([0, 0]), 8) == -1.11670614  # ucc.py:633-637 doctest
+    c = ucc.civector(k["params"])
+    np.testing.assert_allclose(c, k["civector"], atol=k["civector_atol"])
+    e, g = ucc.energy_and_grad(k["params"])
+    assert abs(e - k["e_ucc"]) < 1e-9
+    assert np.abs(g).max() < 1e-7
+    assert abs(ucc.energy([0, 0]) - k["e_hf"]) < 1e-13
+    e_opt = ucc.kernel()
+    assert abs(e_opt - k["e_ucc"]) < 1e-8
+
+
+def test_apply_excitation_doctest_and_statevector_form():
+    k = KAT["apply_excitation"]
+    res = engine_ucc.apply_excitation(k["state"], 4, 2, tuple(k["ex_op"]), hcb=False)
+    assert res.tolist() == k["result"]
+    # statevector in, statevector out (engine_ucc.py:145-159)
+    ci = O.get_ci_strings(4, 2, False)
+    sv = np.zeros(16)
+    sv[ci] = k["state"]
+    out = engine_ucc.apply_excitation(sv, 4, 2, tuple(k["ex_op"]), hcb=False)
+    assert out.shape == (16,) and out[ci].tolist() == k["result"]
+
+
+CASES = [("uccsd", 1, 1), ("uccsd", 2, 2), ("uccsd", 3, 3), ("uccsd", 2, 3), ("uccsd", 3, 1), ("uccsd", 4, 4),
+         ("kupccgsd", 2, 2), ("kupccgsd", 3, 2), ("puccd", 2, 3), ("puccd", 3, 3), ("puccd", 4, 4)]
+
+
+def _build(kind, no, nv):
+    n = no + nv
+    int1e, int2e = random_integral(n)
+    cls = {"uccsd": UCCSD, "kupccgsd": KUPCCGSD, "puccd": PUCCD}[kind]
+    ucc = cls.from_integral(int1e, int2e, 2 * no)
+    return ucc, int1e, int2e
+
+
+@pytest.mark.parametrize("kind,no,nv", CASES)
+def test_energy_grad_civector_against_oracle(kind, no, nv):
+    ucc, int1e, int2e = _build(kind, no, nv)
+    params = _params(ucc.n_params)
+    h = O.get_h_from_integral(int1e, int2e, ucc.n_elec, ucc.hcb)
+    e_ref, g_ref = O.get_energy_and_grad(params, h, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb)
+    c_ref = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb)
+    e, g = ucc.energy_and_grad(params)
+    c = ucc.civector(params)
+    assert np.abs(c - c_ref).max() < C_TOL
+    assert abs(e - e_ref) < E_TOL
+    assert np.abs(g - g_ref).max() < G_TOL
+    assert abs(ucc.energy(params) - e_ref) < E_TOL
+    O.clear_cache()
+
+
+@pytest.mark.parametrize("tag", ["uccsd_2_2", "uccsd_3_3", "uccsd_2_3", "kupccgsd_2_2", "kupccgsd_3_2", "puccd_2_3", "puccd_3_3"])
+def test_against_committed_golden_vectors(tag):
+    kind, no, nv = tag.split("_")
+    ucc, _, _ = _build(kind, int(no), int(nv))
+    params = GOLD[tag + "_params"]
+    e, g = ucc.energy_and_grad(params)
+    c = ucc.civector(params)
+    assert np.abs(c - GOLD[tag + "_civector"]).max() < C_TOL
+    assert abs(e - float(GOLD[tag + "_energy"])) < E_TOL
+    assert np.abs(g - GOLD[tag + "_grad"]).max() < G_TOL
+    sigma = ucc.hamiltonian(c)
+    assert np.abs(sigma - GOLD[tag + "_sigma"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("n,nelec,hcb", [(2, 2, False), (4, 4, False), (4, 2, False), (5, 4, False), (5, 6, False), (6, 6, False), (5, 4, True), (6, 6, True)])
+def test_sigma_against_dense_hamiltonian(n, nelec, hcb):
+    """The GPU H.c against the second-quantised dense matrix (what test_hamiltonian_fcifunc pins upstream)."""
+    int1e, int2e = random_integral(n)
+    h = get_h_from_integral(int1e, int2e, nelec, hcb)
+    dense = bf.dense_hamiltonian_hcb(int1e, int2e, nelec) if hcb else bf.dense_hamiltonian(int1e, int2e, nelec)
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        x = rng.standard_normal(dense.shape[0])
+        assert np.abs(h(x) - dense @ x).max() < 1e-11
+    if not hcb and n <= 4:
+        w = np.linalg.eigvalsh(dense)[0]
+        applied = np.stack([h(np.eye(dense.shape[0])[i]) for i in range(dense.shape[0])], axis=1)
+        assert abs(np.linalg.eigvalsh(0.5 * (applied + applied.T))[0] - w) < 1e-7 * max(1, abs(w))  # rtol of the upstream test
+
+
+def test_sigma_nonsymmetric_integrals():
+    """direct_nosym semantics: no permutational symmetry of int2e is assumed (ucc.py:70-71)."""
+    rng = np.random.default_rng(3)
+    n, nelec = 4, 4
+    int1e = rng.standard_normal((n, n))
+    int2e = rng.standard_normal((n, n, n, n))
+    h_ref = O.get_h_fcifunc_from_integral(int1e, int2e, nelec)
+    h = get_h_from_integral(int1e, int2e, nelec, False)
+    x = rng.standard_normal(36)
+    assert np.abs(h(x) - h_ref(x)).max() < 1e-11
+
+
+def test_every_excitation_kind_single_rotation():
+    """One rotation of each kind (alpha single, beta single, alpha-alpha, beta-beta, alpha-beta, mixed order)
+    on a random vector against the oracle's table form."""
+    n, nelec = 5, 4
+    ops = [(7, 5), (2, 0), (8, 7, 6, 5), (3, 2, 1, 0), (2, 7, 5, 0), (7, 2, 0, 5), (4, 0, 3, 7 + 1), (9, 3, 0, 6), (6, 9, 4, 1)]
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(100)
+    for op in ops:
+        plan = Plan(2 * n, nelec, [op], [0])
+        for theta in (0.3, -1.2):
+            c = plan.civector([theta], init_state=x)
+            c_ref = O.get_civector(np.array([theta]), 2 * n, nelec, [op], [0], init_state=x)
+            assert np.abs(c - c_ref).max() < 1e-14, op
+        g = engine_ucc.apply_excitation(x, 2 * n, nelec, op, hcb=False)
+        assert np.abs(g - O.apply_excitation(x, 2 * n, nelec, op, False)).max() == 0.0, op
+    O.clear_cache()
+
+
+def test_reference_test_excitation_case():
+    """tests/static/test_engine.py:44-71: civector(params) then apply_excitation (4,0,3,7) on an H4-sized space."""
+    ucc, int1e, int2e = _build("uccsd", 2, 2)
+    params = _params(ucc.n_params)
+    state = ucc.apply_excitation(ucc.civector(params), (4, 0, 3, 7))
+    ref = O.apply_excitation(O.get_civector(params, 8, 4, ucc.ex_ops, ucc.param_ids), 8, 4, (4, 0, 3, 7), False)
+    assert np.abs(state - ref).max() < 1e-13
+    dense = bf.dense_excitation_generator((4, 0, 3, 7), 8, 4) @ bf.ucc_state(params, ucc.ex_ops, ucc.param_ids, 8, 4)
+    assert np.abs(state - dense).max() < 1e-12
+
+
+def test_init_state_and_input_not_modified():
+    ucc, int1e, int2e = _build("uccsd", 2, 2)
+    params = _params(ucc.n_params)
+    rng = np.random.default_rng(0)
+    init = rng.standard_normal(36)
+    init /= np.linalg.norm(init)
+    keep = init.copy()
+    ucc.init_state = init
+    e, g = ucc.energy_and_grad(params)
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, 4)
+    e_ref, g_ref = O.get_energy_and_grad(params, h, 8, 4, ucc.ex_ops, ucc.param_ids, init_state=init)
+    assert abs(e - e_ref) < E_TOL and np.abs(g - g_ref).max() < G_TOL
+    np.testing.assert_array_equal(init, keep)  # the reference aliases and mutates; we must not
+    # statevector-form init state (engine_ucc.py:163-174)
+    sv = np.zeros(256)
+    sv[O.get_ci_strings(8, 4, False)] = init
+    ucc.init_state = sv
+    e2, _ = ucc.energy_and_grad(params)
+    assert abs(e2 - e_ref) < E_TOL
+
+
+def test_error_behaviour():
+    ucc, _, _ = _build("uccsd", 2, 2)
+    with pytest.raises(ValueError, match="Incompatible parameter shape"):
+        ucc.energy(np.zeros(3))
+    with pytest.raises(ValueError, match="not supported"):
+        ucc.energy(np.zeros(ucc.n_params), engine="tensornetwork")
+    with pytest.raises(ValueError, match="not supported"):
+        engine_ucc.apply_excitation(np.zeros(36), 8, 4, (5, 0), hcb=False)
+    with pytest.raises(ValueError, match="not supported"):
+        engine_ucc.get_energy_and_grad(np.zeros(1), ucc.hamiltonian, 8, 4, [(1, 1)], [0], False, None)
+    empty = UCC.from_integral(*random_integral(3), 2, ex_ops=[], param_ids=[])
+    assert np.array_equal(empty.civector(np.zeros(0)), np.eye(1, 9)[0])  # no excitations: HF determinant
+    e, g = empty.energy_and_grad(np.zeros(0))
+    assert g.shape == (0,)
+
+
+def test_clear_cache_does_not_change_energy():
+    """tests/test_misc.py:8-13."""
+    ucc, _, _ = _build("uccsd", 2, 2)
+    params = _params(ucc.n_params)
+    e1 = ucc.energy(params)
+    clear_cache()
+    e2 = ucc.energy(params)
+    assert e1 == e2
+
+
+def test_kernel_reaches_fci():
+    """test_gradient_opt / test_ucc upstream: UCCSD reaches FCI for a 4-orbital 4-electron system (atol 1e-4 .. 3e-3)."""
+    int1e, int2e = random_integral(4)
+    # weakly correlated: scale the two-body part so that index 0 is the dominant determinant
+    int1e = int1e + np.diag([-4.0, -3.0, 3.0, 4.0])
+    ucc = UCCSD.from_integral(int1e, int2e, 4)
+    e = ucc.kernel()
+    e_fci = np.linalg.eigvalsh(bf.dense_hamiltonian(int1e, int2e, 4))[0]
+    assert e >= e_fci - 1e-9
+    assert abs(e - e_fci) < 3e-3
+    assert abs(ucc.energy() - e) < 1e-12
+
+
+def test_puccd_matches_explicit_pair_ucc():
+    """tests/static/test_puccd.py:19-58: pUCCD (hcb) == fermionic UCC with explicit paired excitations."""
+    no, nv = 2, 2
+    int1e, int2e = random_integral(4)
+    pu = PUCCD.from_integral(int1e, int2e, 4)
+    params = _params(pu.n_params)
+    paired = [(no + a, 4 + no + a, 4 + i, i) for i in range(no) for a in range(nv - 1, -1, -1)]
+    assert paired[0] == (3, 7, 4, 0)
+    ferm = UCC.from_integral(int1e, int2e, 4, ex_ops=paired, param_ids=list(range(len(paired))))
+    assert abs(pu.energy(params) - ferm.energy(params)) < 1e-10
+
+
+def test_properties_medium_size():
+    """(10e,10o)-size properties the oracle is too slow to check directly in full: norm conservation,
+    <x|H y> symmetry, energy invariance under the reverse sweep bookkeeping (grad vs finite differences)."""
+    n = 8
+    int1e, int2e = random_integral(n)
+    ucc = UCCSD.from_integral(int1e, int2e, n)
+    params = 0.1 * _params(ucc.n_params)
+    c = ucc.civector(params)
+    assert abs(np.linalg.norm(c) - 1.0) < 1e-12
+    rng = np.random.default_rng(2)
+    x, y = rng.standard_normal(c.size), rng.standard_normal(c.size)
+    hx, hy = ucc.hamiltonian(x), ucc.hamiltonian(y)
+    assert abs(y @ hx - x @ hy) < 1e-8 * abs(y @ hx)
+    e, g = ucc.energy_and_grad(params)
+    assert abs(e - c @ ucc.hamiltonian(c)) < 1e-10
+    eps = 1e-5
+    for i in (0, 17, ucc.n_params - 1):
+        d = np.zeros_like(params)
+        d[i] = eps
+        fd = (ucc.energy(params + d) - ucc.energy(params - d)) / (2 * eps)
+        assert abs(fd - g[i]) < 1e-7
+    # oracle on the same inputs (4,900 determinants: seconds on the CPU)
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, n)
+    e_ref, g_ref = O.get_energy_and_grad(params, h, 2 * n, n, ucc.ex_ops, ucc.param_ids)
+    assert abs(e - e_ref) < E_TOL and np.abs(g - g_ref).max() < G_TOL
+    O.clear_cache()
+
+
+def test_device_resident_api():
+    import torch
+
+    ucc, int1e, int2e = _build("uccsd", 3, 3)
+    params = _params(ucc.n_params)
+    plan = Plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids)
+    plan.set_hamiltonian(int1e, int2e)
+    out = torch.empty(plan.size, dtype=torch.float64, device="cuda")
+    plan.civector_dev(params, out)
+    sigma = torch.empty_like(out)
+    plan.apply_h_dev(out, sigma)
+    e_dev = float(out @ sigma)
+    e, g = plan.energy_and_grad_dev(params)
+    assert abs(e - e_dev) < 1e-11
+    c_ref = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids)
+    assert np.abs(out.cpu().numpy() - c_ref).max() < C_TOL
+    assert plan.launch_count > 0
+    O.clear_cache()

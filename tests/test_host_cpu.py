@@ -1,0 +1,147 @@
+"""CPU: host logic of the product package and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import civector_numpy as O
+from oracle import pools
+from tencirchem_b200 import KUPCCGSD, PUCCD, UCCSD, _lib, ci_utils
+from tencirchem_b200.plan import Plan
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+KAT = json.load(open(os.path.join(HERE, "golden", "published_kat.json")))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "tcc_b200.h")).read()
+    declared = set(re.findall(r"\b(tcc_[a-z0-9_]+)\s*\(", header))
+    declared.discard("tcc_plan")
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in _lib.load().tcc_version()
+
+
+def test_ci_strings_bit_exact():
+    k = KAT["ci_strings"]
+    cs, s2a = ci_utils.get_ci_strings(4, 2, False, strs2addr=True)
+    assert cs.tolist() == k["h2_ci_strings"] and s2a.tolist() == k["h2_strs2addr"]
+    assert cs.dtype == np.uint64
+    for nq, ne, hcb in [(8, 4, False), (12, 6, False), (10, 4, False), (16, 8, False), (6, 4, True), (12, 6, True), (4, 0, False)]:
+        a, ta = ci_utils.get_ci_strings(nq, ne, hcb, strs2addr=True)
+        b, tb = O.get_ci_strings(nq, ne, hcb, strs2addr=True)
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(ta, tb)
+    assert ci_utils.get_ex_bitstring(8, 4, (6, 2, 0, 4), False) == k["h4_ex_6204_bitstring"]
+    for bits, addr in k["h2_addr"].items():
+        assert int(ci_utils.get_addr(np.array([int(bits, 2)]), 4, 2, s2a, False)[0]) == addr
+    with pytest.raises(ValueError, match="Too many qubits"):
+        ci_utils.get_ci_strings(64, 2, False)
+    with pytest.raises(ValueError, match="Too many qubits"):
+        Plan(64, 2, (), (), device=None)
+
+
+@pytest.mark.parametrize("no,nv", [(1, 1), (2, 2), (3, 3), (2, 4), (3, 2)])
+def test_excitation_tables_bit_exact(no, nv):
+    """tcc_excitation_tables == get_operators (evolve_civector.py:91-106) for every entry, including the
+    reference's partner index of determinants outside the support."""
+    n = no + nv
+    ops, _ = pools.uccsd_ex_ops(no, nv)
+    gops, _ = pools.kupccgsd_ex_ops(no, nv, 1)
+    extra = [(4, 0, 3, 7), (7, 3, 0, 4), (6, 2, 0, 4), (2, 7, 5, 0)] if n == 4 else []
+    all_ops = list(dict.fromkeys(ops + gops + extra))
+    plan = Plan(2 * n, 2 * no, all_ops, device=None)
+    cs, s2a = O.get_ci_strings(2 * n, 2 * no, False, True)
+    for j, op in enumerate(all_ops):
+        perm, phase, f2 = O.get_operators(2 * n, 2 * no, s2a, op, cs, False)
+        perm2, phase2, f22 = plan.excitation_tables(j)
+        np.testing.assert_array_equal(perm, perm2, err_msg=str(op))
+        np.testing.assert_array_equal(phase.astype(np.int8), phase2, err_msg=str(op))
+        np.testing.assert_array_equal(f2.astype(np.int8), f22, err_msg=str(op))
+
+
+@pytest.mark.parametrize("no,nv", [(1, 1), (2, 2), (3, 4)])
+def test_excitation_tables_hcb_bit_exact(no, nv):
+    n = no + nv
+    ops, pids = pools.puccd_ex_ops(no, nv)
+    plan = Plan(n, 2 * no, ops, pids, hcb=True, device=None)
+    cs, s2a = O.get_ci_strings(n, 2 * no, True, True)
+    for j, op in enumerate(ops):
+        perm, phase, f2 = O.get_operators(n, 2 * no, s2a, op, cs, True)
+        perm2, phase2, f22 = plan.excitation_tables(j)
+        np.testing.assert_array_equal(perm, perm2)
+        np.testing.assert_array_equal(phase.astype(np.int8), phase2)
+        np.testing.assert_array_equal(f2.astype(np.int8), f22)
+
+
+def test_bad_excitations_raise_like_the_reference():
+    for bad in [(1, 1), (0, 1, 1, 2)]:  # evolve_civector.py:92-93
+        with pytest.raises(ValueError, match="not supported"):
+            Plan(8, 4, [bad], device=None)
+    for bad in [(5, 0), (4, 5, 0, 1), (0, 1, 2)]:  # silently wrong upstream / assert at :37
+        with pytest.raises(ValueError, match="not supported"):
+            Plan(8, 4, [bad], device=None)
+    with pytest.raises(ValueError):
+        Plan(8, 4, [(4, 0)], [0, 1], device=None)
+
+
+def test_op_pools_match_published_lists():
+    p = KAT["pools"]
+    int1e, int2e = O.random_integral(2)
+    u = UCCSD(int1e, int2e, 2)
+    assert [list(o) for o in u.ex_ops] == p["uccsd_h2"]["ex_ops"] and u.param_ids == p["uccsd_h2"]["param_ids"]
+    k = KUPCCGSD(int1e, int2e, 2)
+    assert [list(o) for o in k.ex_ops] == p["kupccgsd_h2"]["ex_ops"] and k.param_ids == p["kupccgsd_h2"]["param_ids"]
+    pu = PUCCD(int1e, int2e, 2)
+    assert [list(o) for o in pu.ex_ops] == p["puccd_h2"]["ex_ops"] and pu.param_ids == p["puccd_h2"]["param_ids"]
+    int1e, int2e = O.random_integral(4)
+    u = UCCSD(int1e, int2e, 4)
+    o1, i1, _ = u.get_ex1_ops()
+    o2, i2, _ = u.get_ex2_ops()
+    assert [list(o) for o in o1] == p["h4_ex1"]["ex_ops"] and i1 == p["h4_ex1"]["param_ids"]
+    assert [list(o) for o in o2] == p["h4_ex2"]["ex_ops"] and i2 == p["h4_ex2"]["param_ids"]
+    for no, nv in [(2, 2), (3, 5), (4, 4)]:
+        i1, i2 = np.zeros((no + nv,) * 2), np.zeros((no + nv,) * 4)
+        u = UCCSD(i1, i2, 2 * no)
+        assert (u.ex_ops, u.param_ids) == tuple(pools.uccsd_ex_ops(no, nv))
+        k = KUPCCGSD(i1, i2, 2 * no)
+        assert (k.ex_ops, k.param_ids) == tuple(pools.kupccgsd_ex_ops(no, nv, 3))
+        pu = PUCCD(i1, i2, 2 * no)
+        assert (pu.ex_ops, pu.param_ids) == tuple(pools.puccd_ex_ops(no, nv))
+
+
+def test_sizes_at_baseline_configs():
+    """SURVEY.md section 8 size table: (n, M, P) of unscreened UCCSD."""
+    for n, m, p, size in [(4, 26, 15, 36), (8, 360, 188, 4900), (12, 1818, 927, 853776), (16, 5792, 2928, 165636900)]:
+        ops, pids = pools.uccsd_ex_ops(n // 2, n // 2)
+        assert len(ops) == m and max(pids) + 1 == p
+        u = UCCSD(np.zeros((n, n)), np.zeros((n,) * 4), n)
+        assert u.civector_size == size and len(u.ex_ops) == m and u.n_params == p
+
+
+def test_no_cpu_fallback():
+    """Compute entry points must fail loudly without a GPU instead of silently computing on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    plan = Plan(4, 2, [(3, 2), (1, 0), (1, 3, 2, 0)], [0, 0, 1], device=None)
+    with pytest.raises(_lib.EngineUnavailable):
+        plan.civector(np.zeros(2))
+    with pytest.raises(_lib.EngineUnavailable):
+        Plan(4, 2, [(3, 2)], [0], device=0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tencirchem_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".hpp", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f

@@ -1,0 +1,189 @@
+"""CPU: pins the oracle against every PySCF-free known-answer value the reference publishes for this
+path (tests/golden/published_kat.json) and against the independent brute-force
+second oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bruteforce as bf
+from oracle import civector_numpy as O
+from oracle import pools
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "published_kat.json")))
+
+
+def h2_integrals():
+    k = KAT["h2_sto3g"]
+    int1e = np.diag([k["h00"], k["h11"]])
+    int2e = np.zeros((2, 2, 2, 2))
+    int2e[0, 0, 0, 0] = k["J00"]
+    int2e[1, 1, 1, 1] = k["J11"]
+    int2e[0, 0, 1, 1] = int2e[1, 1, 0, 0] = k["J01"]
+    for idx in [(0, 1, 0, 1), (0, 1, 1, 0), (1, 0, 0, 1), (1, 0, 1, 0)]:
+        int2e[idx] = k["K01"]
+    return int1e, int2e
+
+
+def test_ci_string_doctests():
+    k = KAT["ci_strings"]
+    cs, s2a = O.get_ci_strings(4, 2, False, strs2addr=True)
+    assert cs.tolist() == k["h2_ci_strings"]
+    assert s2a.tolist() == k["h2_strs2addr"]
+    for bits, addr in k["h2_addr"].items():
+        assert int(O.get_addr(np.array([int(bits, 2)], dtype=np.uint64), 4, 2, s2a, False)[0]) == addr
+    cs_h, s2a_h = O.get_ci_strings(2, 2, True, strs2addr=True)
+    for bits, addr in k["h2_hcb_addr"].items():
+        assert int(O.get_addr(np.array([int(bits, 2)], dtype=np.uint64), 2, 2, s2a_h, True)[0]) == addr
+    # faq.rst:38-43: HF determinant and one excited determinant of H4
+    assert format(int(O.get_ci_strings(8, 4, False)[0]), "08b") == k["h4_hf_bitstring"]
+    assert O.get_ex_bitstring(8, 4, (6, 2, 0, 4), False) == k["h4_ex_6204_bitstring"]
+
+
+def test_too_many_qubits():
+    with pytest.raises(ValueError, match="Too many qubits"):
+        O.get_ci_strings(64, 2, False)
+
+
+def test_apply_excitation_doctest():
+    k = KAT["apply_excitation"]
+    res = O.apply_excitation(np.array(k["state"], dtype=float), 4, 2, tuple(k["ex_op"]), False)
+    assert res.tolist() == k["result"]
+
+
+def test_pool_doctests():
+    p = KAT["pools"]
+    ops, ids = pools.uccsd_ex_ops(1, 1)
+    assert [list(o) for o in ops] == p["uccsd_h2"]["ex_ops"] and ids == p["uccsd_h2"]["param_ids"]
+    ops, ids = pools.kupccgsd_ex_ops(1, 1, 3)
+    assert [list(o) for o in ops] == p["kupccgsd_h2"]["ex_ops"] and ids == p["kupccgsd_h2"]["param_ids"]
+    ops, ids = pools.puccd_ex_ops(1, 1)
+    assert [list(o) for o in ops] == p["puccd_h2"]["ex_ops"] and ids == p["puccd_h2"]["param_ids"]
+    ops, ids = pools.ex1_ops(2, 2)
+    assert [list(o) for o in ops] == p["h4_ex1"]["ex_ops"] and ids == p["h4_ex1"]["param_ids"]
+    ops, ids = pools.ex2_ops(2, 2)
+    assert [list(o) for o in ops] == p["h4_ex2"]["ex_ops"] and ids == p["h4_ex2"]["param_ids"]
+
+
+def test_h2_published_state_and_energy():
+    k = KAT["h2_sto3g"]
+    int1e, int2e = h2_integrals()
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, 2)
+    ops = [tuple(o) for o in k["ex_ops"]]
+    params = np.array(k["params"])
+    c = O.get_civector(params, 4, 2, ops, k["param_ids"])
+    np.testing.assert_allclose(c, k["civector"], atol=k["civector_atol"])
+    e, g = O.get_energy_and_grad(params, h, 4, 2, ops, k["param_ids"])
+    assert abs(e + k["e_nuc"] - k["e_ucc"]) < 1e-9  # published params are rounded to 9 digits
+    assert np.abs(g).max() < 1e-7  # the published point is the optimum
+    e_hf = O.get_energy(np.zeros(2), h, 4, 2, ops, k["param_ids"])
+    assert abs(e_hf + k["e_nuc"] - k["e_hf"]) < 1e-13
+    # the nocache ("civector-large") engine gives the same numbers
+    e2, g2 = O.get_energy_and_grad_nocache(params, h, 4, 2, ops, k["param_ids"])
+    assert abs(e - e2) < 1e-14 and np.abs(g - g2).max() < 1e-14
+
+
+def _all_test_ops(no, nv):
+    ops, _ = pools.uccsd_ex_ops(no, nv)
+    gops, _ = pools.kupccgsd_ex_ops(no, nv, 1)
+    extra = [(4, 0, 3, 7), (7, 3, 0, 4), (6, 2, 0, 4), (2, 7, 5, 0)] if no + nv == 4 else []
+    return list(dict.fromkeys(ops + gops + extra))
+
+
+@pytest.mark.parametrize("no,nv", [(1, 1), (2, 2), (2, 3), (3, 3)])
+def test_sign_rule_closed_form_matches_jordan_wigner(no, nv):
+    for op in _all_test_ops(no, nv):
+        assert O.fermion_phase_mask_and_sign(op) == O.fermion_phase_closed_form(op), op
+
+
+@pytest.mark.parametrize("no,nv", [(2, 2), (3, 3), (2, 3)])
+def test_tables_are_matrix_elements_of_G(no, nv):
+    """fket_phase[I] == <I| T - T^+ |perm(I)> and f2 == diag(G^2), against brute force."""
+    n = no + nv
+    cs, s2a = O.get_ci_strings(2 * n, 2 * no, False, True)
+    for op in _all_test_ops(no, nv):
+        perm, phase, f2 = O.get_operators(2 * n, 2 * no, s2a, op, cs, False)
+        g = bf.dense_excitation_generator(op, 2 * n, 2 * no)
+        dense = np.zeros_like(g)
+        dense[np.arange(len(cs)), perm.astype(np.int64)] = phase
+        # rows outside the support have phase 0 whatever their (meaningless) partner index
+        np.testing.assert_array_equal(dense, g, err_msg=str(op))
+        np.testing.assert_array_equal(np.diag(g @ g), f2, err_msg=str(op))
+
+
+def test_hcb_tables_against_brute_force():
+    cs, s2a = O.get_ci_strings(5, 4, True, True)
+    ops, _ = pools.puccd_ex_ops(2, 3)
+    for op in ops + [(1, 3), (4, 0)]:
+        perm, phase, f2 = O.get_operators(5, 4, s2a, op, cs, True)
+        g = bf.dense_excitation_generator_hcb(op, 5, 4)
+        dense = np.zeros_like(g)
+        dense[np.arange(len(cs)), perm.astype(np.int64)] = phase
+        np.testing.assert_array_equal(dense, g)
+
+
+@pytest.mark.parametrize("no,nv", [(2, 2), (2, 3)])
+def test_state_matches_expm_product(no, nv):
+    n = no + nv
+    ops, pids = pools.uccsd_ex_ops(no, nv)
+    np.random.seed(7)
+    params = np.random.rand(max(pids) + 1) - 0.5
+    c = O.get_civector(params, 2 * n, 2 * no, ops, pids)
+    c_bf = bf.ucc_state(params, ops, pids, 2 * n, 2 * no)
+    assert np.abs(c - c_bf).max() < 1e-13
+    c2 = O.get_civector_nocache(params, 2 * n, 2 * no, ops, pids)
+    assert np.abs(c - c2).max() < 1e-15
+
+
+@pytest.mark.parametrize("n,nelec", [(2, 2), (4, 4), (4, 2), (5, 4)])
+def test_sigma_equals_dense_hamiltonian(n, nelec):
+    """test_hamiltonian_fcifunc (tests/static/test_hamiltonian.py:44-64) pins the lowest eigenvalue; here the
+    whole matrix is checked against the second-quantised definition of hamiltonian.py:51-96."""
+    int1e, int2e = O.random_integral(n)
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, nelec)
+    dense = bf.dense_hamiltonian(int1e, int2e, nelec)
+    dim = dense.shape[0]
+    applied = np.stack([h(np.eye(dim)[i]) for i in range(dim)], axis=1)
+    assert np.abs(applied - dense).max() < 1e-12
+    if (n, nelec) == (4, 4):
+        # session-derived check value recorded in SURVEY.md appendix
+        assert abs(np.linalg.eigvalsh(dense)[0] - (-5.118408240910737)) < 1e-12
+
+
+def test_sigma_hcb_equals_dense():
+    int1e, int2e = O.random_integral(5)
+    h = O.get_h_fcifunc_hcb_from_integral(int1e, int2e, 4)
+    dense = bf.dense_hamiltonian_hcb(int1e, int2e, 4)
+    dim = dense.shape[0]
+    applied = np.stack([h(np.eye(dim)[i]) for i in range(dim)], axis=1)
+    assert np.abs(applied - dense).max() < 1e-12
+
+
+def test_random_44_check_values_and_gradient():
+    int1e, int2e = O.random_integral(4)
+    ops, pids = pools.uccsd_ex_ops(2, 2)
+    np.random.seed(2077)
+    params = np.random.rand(15) - 0.5
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, 4)
+    e, g = O.get_energy_and_grad(params, h, 8, 4, ops, pids)
+    assert abs(e - 0.06402312039336584) < 1e-12
+    eps = 1e-6
+    fd = np.zeros_like(g)
+    for i in range(len(params)):
+        d = np.zeros_like(params)
+        d[i] = eps
+        fd[i] = (O.get_energy(params + d, h, 8, 4, ops, pids) - O.get_energy(params - d, h, 8, 4, ops, pids)) / (2 * eps)
+    assert np.abs(fd - g).max() < 1e-8
+
+
+def test_golden_file_is_current():
+    """The committed fixtures are what the oracle produces today."""
+    gold = np.load(os.path.join(HERE, "golden", "oracle_vectors.npz"))
+    int1e, int2e = O.random_integral(5)
+    ops, pids = pools.uccsd_ex_ops(2, 3)
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, 4)
+    e, g = O.get_energy_and_grad(gold["uccsd_2_3_params"], h, 10, 4, ops, pids)
+    assert abs(e - float(gold["uccsd_2_3_energy"])) < 1e-13
+    np.testing.assert_allclose(g, gold["uccsd_2_3_grad"], atol=1e-13)

@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 civector UCC engine: UCCSD energy_and_grad evaluations/s.
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload 16o|12o|8o|4o]
+* a "step" is ONE energy_and_grad evaluation (forward sweep, H.c, energy, reverse sweep, all gradients)
+  of unscreened UCCSD in generator order on synthetic inputs: random_integral(n, seed 2077) as MO
+  integrals, theta = rand(P) - 0.5 with seed 2077 + step.
+* default workload: (16e,16o), N = 165,636,900 determinants, M = 5792 excitations, P = 2928 parameters
+  (BASELINE.json configs[3], the size its target is quoted on; a 1.3 GB vector >> the 126 MB L2, so no
+  explicit L2 flush is needed between steps).
+* N > 1: every rank evaluates its own theta set (batched parameter sets shard trivially; no data-path
+  collective), `value` = all ranks' evaluations / max-over-ranks time, scaling "weak".
+* `--impl reference`: the CPU oracle port of the reference numpy engine (oracle/civector_numpy.py; the
+  Python reference itself cannot be imported here -- DESIGN.md) timed on a bounded sample, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {"16o": 16, "14o": 14, "12o": 12, "10o": 10, "8o": 8, "4o": 4}
+METRIC = "uccsd_energy_and_grad_evals_per_s"
+
+
+def workload_desc(n):
+    return f"UCCSD energy_and_grad ({n}e,{n}o), random_integral seed 2077, unscreened generator order"
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_sample(n, n_ops_sample=2):
+    """Times the oracle port of the reference numpy engine (nocache / 'civector-large' form, which is what
+    the reference selects above 16 qubits, ucc.py:233-239) on a bounded sample and extrapolates to one
+    energy_and_grad evaluation by operation counts."""
+    from oracle import civector_numpy as O
+    from oracle import pools
+
+    no = n // 2
+    ops, pids = pools.uccsd_ex_ops(no, n - no)
+    m = len(ops)
+    nq = 2 * n
+    t0 = time.perf_counter()
+    ci_strings, strs2addr = O.get_ci_strings(nq, n, False, strs2addr=True)
+    t_strings = time.perf_counter() - t0
+    size = len(ci_strings)
+    rng = np.random.default_rng(0)
+    ket = rng.standard_normal(size)
+    bra = rng.standard_normal(size)
+    # one op of each cost class is enough for the reference: its [N] tables make every excitation cost the same
+    picks = [ops[0], ops[len(ops) // 3], ops[-1]][:n_ops_sample] if n_ops_sample <= 3 else ops[:n_ops_sample]
+    _ = bra[:1024] @ ket[:1024]  # spin up BLAS threads outside the timed sample
+    t_tab = t_fwd = t_rev = 0.0
+    for f_idx in picks:
+        t0 = time.perf_counter()
+        perm, phase, f2 = O.get_operators(nq, n, strs2addr, tuple(f_idx), ci_strings, False)
+        t1 = time.perf_counter()
+        ket = O.evolve_excitation(ket, perm, phase, f2, 1 - np.cos(0.3), np.sin(0.3))
+        t2 = time.perf_counter()
+        bra = O.evolve_excitation(bra, perm, phase, f2, 1 - np.cos(0.3), -np.sin(0.3))
+        ket = O.evolve_excitation(ket, perm, phase, f2, 1 - np.cos(0.3), -np.sin(0.3))
+        _ = bra @ (ket[perm] * phase)
+        t3 = time.perf_counter()
+        t_tab += t1 - t0
+        t_fwd += t2 - t1
+        t_rev += t3 - t2
+        del perm, phase, f2
+    k = len(picks)
+    t_tab, t_fwd, t_rev = t_tab / k, t_fwd / k, t_rev / k
+    del ket, bra, ci_strings
+    # H.c: the oracle's Knowles-Handy port at a size that fits, scaled by the 2 n^4 N flop count
+    ns = min(n, 10)
+    i1, i2 = O.random_integral(ns)
+    h = O.get_h_fcifunc_from_integral(i1, i2, ns)
+    from math import comb
+    x = rng.standard_normal(comb(ns, ns // 2) ** 2)
+    h(x)
+    t0 = time.perf_counter()
+    h(x)
+    t_sig_small = time.perf_counter() - t0
+    scale = (n**4 * comb(n, n // 2) ** 2) / (ns**4 * comb(ns, ns // 2) ** 2)
+    t_sigma = t_sig_small * scale
+    # civector-large rebuilds the tables in both sweeps (evolve_civector.py:253-308); up to 16 qubits the
+    # reference defaults to the cached-table engine (ucc.py:233-239) and the build is staging, not per call
+    cached = nq <= 16
+    t_eval = m * ((0.0 if cached else t_tab) + t_fwd) + t_sigma + m * ((0.0 if cached else t_tab) + t_rev)
+    sample = (f"{k} of {m} excitations at full size N={size} (table build {t_tab:.2f}s, rotation {t_fwd:.2f}s, reverse step "
+              f"{t_rev:.2f}s each; strings {t_strings:.1f}s) + H.c timed at ({ns}e,{ns}o) = {t_sig_small:.2f}s scaled x{scale:.0f} by 2n^4N; "
+              f"extrapolated by operation counts to one evaluation = {t_eval:.0f}s")
+    threads = os.cpu_count() or 1
+    return {"value": 1.0 / t_eval, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample,
+            "note": "numpy gather/elementwise is single-threaded as in the reference; BLAS threads only in H.c"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = WORKLOADS[args.workload]
+    res = None
+    times = []
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = cpu_reference_sample(n, n_ops_sample=1 if step < args.warmup else 2)
+        if step >= args.warmup:
+            times.append(1.0 / res["value"])
+    t_eval = float(np.mean(times))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": 1.0 / t_eval, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_eval, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_desc(n), "note": "CPU oracle port of the reference numpy engine; each step is a bounded sample extrapolated by operation counts"},
+        "cpu_baseline": {**res, "value": 1.0 / t_eval},
+        "e2e": {"value": 1.0 / t_eval, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from tencirchem_b200 import UCCSD
+    from tencirchem_b200.evolve_civector import _bind_hamiltonian, get_plan
+    from tencirchem_b200.hamiltonian import random_integral
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = WORKLOADS[args.workload]
+    int1e, int2e = random_integral(n)
+    ucc = UCCSD.from_integral(int1e, int2e, n)
+    m, p_count = len(ucc.ex_ops), ucc.n_params
+    size = ucc.civector_size
+
+    t0 = time.perf_counter()
+    plan = get_plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False, device=local_rank)
+    _bind_hamiltonian(plan, ucc.hamiltonian)
+    staging_s = time.perf_counter() - t0
+
+    def theta(step):
+        np.random.seed(2077 + step + 1000 * rank)
+        return np.random.rand(p_count) - 0.5
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the public API call a user makes; it must route to the same plan (module-level plan cache)
+    import tencirchem_b200.evolve_civector as ev
+    if local_rank != 0:
+        # the ansatz classes use device 0 of the process by default; make the cached plan the rank's device
+        ev._PLAN_CACHE[(ucc.n_qubits, ucc.n_elec, tuple(tuple(o) for o in ucc.ex_ops), tuple(ucc.param_ids), False, 0)] = plan
+
+    for w in range(args.warmup):
+        plan.energy_and_grad_dev(theta(-1 - w))
+    barrier()
+
+    # ---- device-timed region: K evaluations, vectors resident in HBM, CUDA events on the launch stream
+    plan.profile_enable(True)
+    launches0 = plan.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    last = None
+    for k in range(args.steps):
+        last = plan.energy_and_grad_dev(theta(k))
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = plan.profile_read()
+    plan.profile_enable(False)
+    launches = plan.launch_count - launches0
+
+    # ---- end-to-end region: the public API with host buffers (params in, energy + gradient out)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e_host, g_host = ucc.energy_and_grad(theta(k))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert abs(e_host - last[0]) < 1e-9 * max(1.0, abs(e_host)), (e_host, last[0])
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    evals = args.steps * world
+    value = evals / (dev_ms * 1e-3)
+    e2e_value = evals / (e2e_ms * 1e-3)
+    peak, peak_src = measured_peak_hbm()
+    # dominant kernel = the slot with the largest device time
+    dom = max(prof, key=lambda s: prof[s][0])
+    d_ms, d_launch, d_bytes = prof[dom]
+    achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+    kernel_names = {"rev_alphabeta": "reverse_kernel<false,false>", "rev_alpha": "reverse_kernel<false,true>",
+                    "rev_beta": "reverse_kernel<true,false>", "fwd_alphabeta": "rotate_kernel<false,false>",
+                    "fwd_alpha": "rotate_kernel<false,true>", "fwd_beta": "rotate_kernel<true,false>",
+                    "sigma_ab": "sigma_ab_kernel", "sigma_ss": "spmm_rows_kernel+transpose_kernel", "dot": "dot_kernel"}
+    total_prof_ms = sum(v[0] for v in prof.values())
+    phases = {s: {"ms_per_step": round(v[0] / args.steps, 3), "launches_per_step": v[1] // args.steps,
+                  "algorithmic_GBps": round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 else None,
+                  "share": round(v[0] / total_prof_ms, 4) if total_prof_ms else None} for s, v in prof.items()}
+    dense_bytes = (48 * m + 16) * size
+    line = {
+        "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_desc(n), "n_determinants": size, "n_excitations": m, "n_params": p_count,
+                   "l2": "inputs larger than L2 (1.3 GB vectors vs 126 MB)" if size * 8 > 2.5e8 else "vectors fit in L2; no flush",
+                   "multi_gpu": "independent theta sets per rank, no data-path collective" if world > 1 else "single GPU",
+                   "staging_s": round(staging_s, 2)},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": 8 * p_count, "d2h_bytes_per_step": 8 * (m + 1),
+                "note": "public API UCCSD.energy_and_grad(params): host params in, host (energy, gradient) out; the CI vectors never leave HBM"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": kernel_names.get(dom, dom), "phase": dom, "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "avg_launch_us": 1e3 * d_ms / max(d_launch, 1), "launches": d_launch,
+                     "algorithmic_bytes_per_launch": d_bytes / max(d_launch, 1)},
+        "effective_dense_model_GBps": dense_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
+        "phases": phases,
+        "clocks": clocks,
+        "energy_last_step": last[0],
+    }
+    if not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_reference_sample(n, n_ops_sample=2)
+        except Exception as exc:  # pragma: no cover
+            line["cpu_baseline"] = {"error": repr(exc)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="16o", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -114,13 +114,30 @@ int tcc_apply_excitation_host(tcc_plan* plan, const double* c_host, const int32_
 /* ---- building blocks (used by the sharded multi-GPU driver and the benchmarks) ------------ */
 /* one UCC factor exp(theta G_j) applied in place to a device vector */
 int tcc_rotate(tcc_plan* plan, int j, double theta, double* c_dev, void* stream);
-/* reverse-sweep step for excitation j: ket,bra <- exp(-theta G_j); *grad_dev += <bra|G_j|ket> */
+/* reverse-sweep step for excitation j: ket,bra <- exp(-theta G_j); *grad_dev = <bra|G_j|ket> (overwritten) */
 int tcc_reverse_step(tcc_plan* plan, int j, double theta, double* ket_dev, double* bra_dev,
                      double* grad_dev /* one double on the device */, void* stream);
 /* algorithmic CI-vector bytes one rotation of excitation j must move: 16 * |support_j| */
 int64_t tcc_op_support_bytes(const tcc_plan* plan, int j);
 /* kernel launches issued by this plan since creation (for bench.py's gpu_launches) */
 int64_t tcc_launch_count(const tcc_plan* plan);
+
+/* ---- per-phase device timing (CUDA events on the call's stream, recorded only where the phase
+ * changes).  Slots: forward rotations by kind, reverse-sweep steps by kind, the same-spin and
+ * opposite-spin parts of H.c, the energy dot product.  `bytes` are ALGORITHMIC CI-vector bytes
+ * (DESIGN.md): 32 per rotated pair, 64 per reverse-sweep pair, vector passes for the rest. */
+#define TCC_PROF_FWD_BETA 0
+#define TCC_PROF_FWD_ALPHA 1
+#define TCC_PROF_FWD_ALPHABETA 2
+#define TCC_PROF_REV_BETA 3
+#define TCC_PROF_REV_ALPHA 4
+#define TCC_PROF_REV_ALPHABETA 5
+#define TCC_PROF_SIGMA_SS 6
+#define TCC_PROF_SIGMA_AB 7
+#define TCC_PROF_DOT 8
+#define TCC_PROF_SLOTS 9
+int tcc_profile_enable(tcc_plan* plan, int on); /* also resets the accumulators */
+int tcc_profile_read(tcc_plan* plan, double* ms /*[TCC_PROF_SLOTS]*/, int64_t* launches, int64_t* bytes);
 
 #ifdef __cplusplus
 }

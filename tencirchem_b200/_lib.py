@@ -51,7 +51,11 @@ SIGNATURES = {
     "tcc_reverse_step": (C.c_int, [_p, C.c_int, C.c_double, _p, _p, _p, _p]),
     "tcc_op_support_bytes": (C.c_int64, [_p, C.c_int]),
     "tcc_launch_count": (C.c_int64, [_p]),
+    "tcc_profile_enable": (C.c_int, [_p, C.c_int]),
+    "tcc_profile_read": (C.c_int, [_p, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
+
+PROF_SLOTS = ("fwd_beta", "fwd_alpha", "fwd_alphabeta", "rev_beta", "rev_alpha", "rev_alphabeta", "sigma_ss", "sigma_ab", "dot")
 
 _lib = None
 

@@ -40,8 +40,63 @@ struct DevHop {
     int len = 0;
 };
 
+// Per-phase device timing: CUDA events are recorded only where the phase (slot) changes, so a run of
+// thousands of identical launches costs two events.  Slots are listed in include/tcc_b200.h.
+struct Profiler {
+    bool on = false;
+    int cur = -1;
+    std::vector<cudaEvent_t> pool;
+    std::vector<std::pair<int, int>> marks;  // (slot, event index)
+    size_t used = 0;
+    double ms[TCC_PROF_SLOTS] = {0};
+    int64_t launches[TCC_PROF_SLOTS] = {0};
+    int64_t bytes[TCC_PROF_SLOTS] = {0};
+    cudaEvent_t next_event() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void mark(int slot, cudaStream_t st) {
+        if (!on || slot == cur) return;
+        cudaEvent_t e = next_event();
+        cudaEventRecord(e, st);
+        marks.push_back({slot, int(used) - 1});
+        cur = slot;
+    }
+    void count(int slot, int64_t nlaunch, int64_t nbytes) {
+        if (!on) return;
+        launches[slot] += nlaunch;
+        bytes[slot] += nbytes;
+    }
+    // call after the stream has been synchronised
+    void resolve() {
+        if (!on) return;
+        for (size_t i = 0; i + 1 < marks.size(); ++i) {
+            float t = 0.f;
+            if (marks[i].first >= 0 && cudaEventElapsedTime(&t, pool[marks[i].second], pool[marks[i + 1].second]) == cudaSuccess)
+                ms[marks[i].first] += t;
+        }
+        marks.clear();
+        used = 0;
+        cur = -1;
+    }
+    void reset() {
+        for (int i = 0; i < TCC_PROF_SLOTS; ++i) ms[i] = 0, launches[i] = 0, bytes[i] = 0;
+        marks.clear();
+        used = 0;
+        cur = -1;
+    }
+    ~Profiler() {
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+
 struct tcc_plan {
     HostPlan hp;
+    Profiler prof;
     int device = 0;
     std::vector<DevHop> dhops;
     double* ket = nullptr;
@@ -330,14 +385,20 @@ static int apply_h_impl(tcc_plan* p, const double* c, double* sigma, cudaStream_
     }
     if (int rc = ensure_vec(p, &p->ws1)) return rc;
     if (int rc = ensure_vec(p, &p->ws2)) return rc;
+    const int64_t vec = hp.N * 8;
     // alpha-alpha: sigma(a', :) = sum_a Hss[a', a] c(a, :)
+    p->prof.mark(TCC_PROF_SIGMA_SS, st);
     launch_spmm_rows(c, sigma, hp.na, hp.nb, p->d_ell_col, p->d_ell_val, hp.ell_width, false, st);
     // beta-beta on the transposed matrix, then added back transposed
     launch_transpose(c, p->ws1, hp.na, hp.nb, false, st);
     launch_spmm_rows(p->ws1, p->ws2, hp.nb, hp.na, p->d_ell_col, p->d_ell_val, hp.ell_width, false, st);
     launch_transpose(p->ws2, sigma, hp.nb, hp.na, true, st);
+    p->prof.count(TCC_PROF_SIGMA_SS, 4, 9 * vec);  // 2+2+2+3 vector passes
     // alpha-beta on the FP64 tensor path
+    p->prof.mark(TCC_PROF_SIGMA_AB, st);
     launch_sigma_ab(c, sigma, hp.na, hp.nb, p->d_links, hp.ml, p->d_w, hp.n, p->n2p, st);
+    p->prof.count(TCC_PROF_SIGMA_AB, (hp.na + 65534) / 65535, 3 * vec);
+    p->prof.mark(-1, st);
     p->launches += 4 + (hp.na + 65534) / 65535;
     return 0;
 }
@@ -354,7 +415,9 @@ int tcc_apply_h(tcc_plan* p, const double* c_dev, double* sigma_dev, void* strea
 
 static void rotate_op(tcc_plan* p, int j, double theta, double* c, cudaStream_t st) {
     const OpDesc& op = p->hp.ops[j];
+    p->prof.mark(TCC_PROF_FWD_BETA + op.kind, st);
     launch_rotate(c, p->hp.nb, row_side(p, op), col_side(p, op), std::cos(theta), std::sin(theta) * op.s0, st);
+    p->prof.count(TCC_PROF_FWD_BETA + op.kind, 1, 32 * p->hp.support_pairs(op));
     p->launches += 1;
 }
 
@@ -367,6 +430,7 @@ static int civector_impl(tcc_plan* p, const double* params, const double* init_d
         p->launches += 1;
     }
     for (size_t j = 0; j < hp.ops.size(); ++j) rotate_op(p, int(j), params[hp.ops[j].param], out, st);
+    p->prof.mark(-1, st);
     return 0;
 }
 
@@ -390,8 +454,10 @@ int tcc_rotate(tcc_plan* p, int j, double theta, double* c_dev, void* stream) {
 
 static void reverse_op(tcc_plan* p, int j, double theta, double* ket, double* bra, double* grad_out, cudaStream_t st) {
     const OpDesc& op = p->hp.ops[j];
+    p->prof.mark(TCC_PROF_REV_BETA + op.kind, st);
     launch_reverse(ket, bra, p->hp.nb, row_side(p, op), col_side(p, op), std::cos(theta), -std::sin(theta) * op.s0,
                    double(op.s0), p->partials, p->ticket, grad_out, st);
+    p->prof.count(TCC_PROF_REV_BETA + op.kind, 1, 64 * p->hp.support_pairs(op));
     p->launches += 1;
 }
 
@@ -412,14 +478,19 @@ static int energy_impl(tcc_plan* p, const double* params, const double* init_dev
     if (int rc = civector_impl(p, params, init_dev, p->ket, st)) return rc;
     if (int rc = apply_h_impl(p, p->ket, p->bra, st)) return rc;
     const int m = int(hp.ops.size());
+    p->prof.mark(TCC_PROF_DOT, st);
     launch_dot(p->bra, p->ket, hp.N, p->partials, p->ticket, p->grad_ops + m, st);
+    p->prof.count(TCC_PROF_DOT, 1, 16 * hp.N);
+    p->prof.mark(-1, st);
     p->launches += 1;
     if (grad) {
         for (int j = m - 1; j >= 0; --j) reverse_op(p, j, params[hp.ops[j].param], p->ket, p->bra, p->grad_ops + j, st);
     }
     int first = grad ? 0 : m;
+    p->prof.mark(-1, st);
     CUDA_TRY(cudaMemcpyAsync(p->pinned + first, p->grad_ops + first, sizeof(double) * (m + 1 - first), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    p->prof.resolve();
     CUDA_TRY(cudaGetLastError());
     *energy = p->pinned[m];
     if (grad) {
@@ -459,6 +530,23 @@ int tcc_apply_excitation(tcc_plan* p, const double* c_dev, const int32_t* ex_op,
     launch_apply_g(c_dev, out_dev, p->hp.nb, row_side(p, op), col_side(p, op), double(op.s0), st);
     p->launches += 1;
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int tcc_profile_enable(tcc_plan* p, int on) {
+    if (!p) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    p->prof.on = on != 0;
+    p->prof.reset();
+    return 0;
+}
+
+int tcc_profile_read(tcc_plan* p, double* ms, int64_t* launches, int64_t* bytes) {
+    if (!p || !ms || !launches || !bytes) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    for (int i = 0; i < TCC_PROF_SLOTS; ++i) {
+        ms[i] = p->prof.ms[i];
+        launches[i] = p->prof.launches[i];
+        bytes[i] = p->prof.bytes[i];
+    }
     return 0;
 }
 

@@ -92,6 +92,22 @@ class Plan:
     def device_bytes(self) -> int:
         return int(self.lib.tcc_plan_device_bytes(self.handle))
 
+    def profile_enable(self, on=True):
+        _lib.check(self.lib.tcc_profile_enable(self.handle, int(bool(on))))
+
+    def profile_read(self):
+        """{slot: (ms, launches, algorithmic_bytes)} accumulated since ``profile_enable``."""
+        k = len(_lib.PROF_SLOTS)
+        ms = np.zeros(k, dtype=np.float64)
+        launches = np.zeros(k, dtype=np.int64)
+        nbytes = np.zeros(k, dtype=np.int64)
+        _lib.check(
+            self.lib.tcc_profile_read(
+                self.handle, _dptr(ms), launches.ctypes.data_as(C.POINTER(C.c_int64)), nbytes.ctypes.data_as(C.POINTER(C.c_int64))
+            )
+        )
+        return {name: (float(ms[i]), int(launches[i]), int(nbytes[i])) for i, name in enumerate(_lib.PROF_SLOTS)}
+
     # ---- Hamiltonian ----
     def set_hamiltonian(self, int1e, int2e, token=None):
         n = self.n_qubits if self.hcb else self.n_qubits // 2

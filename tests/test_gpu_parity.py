@@ -156,7 +156,7 @@ def test_every_excitation_kind_single_rotation():
     """One rotation of each kind (alpha single, beta single, alpha-alpha, beta-beta, alpha-beta, mixed order)
     on a random vector against the oracle's table form."""
     n, nelec = 5, 4
-    ops = [(7, 5), (2, 0), (8, 7, 6, 5), (3, 2, 1, 0), (2, 7, 5, 0), (7, 2, 0, 5), (4, 0, 3, 7 + 1), (9, 3, 0, 6), (6, 9, 4, 1)]
+    ops = [(7, 5), (2, 0), (8, 7, 6, 5), (3, 2, 1, 0), (2, 7, 5, 0), (7, 2, 0, 5), (5, 0, 3, 7), (9, 3, 0, 6), (6, 9, 8, 5)]
     rng = np.random.default_rng(5)
     x = rng.standard_normal(100)
     for op in ops:
@@ -225,7 +225,7 @@ def test_clear_cache_does_not_change_energy():
     e1 = ucc.energy(params)
     clear_cache()
     e2 = ucc.energy(params)
-    assert e1 == e2
+    assert abs(e1 - e2) < 1e-12  # sigma accumulates with fp64 atomics: last-bit differences run to run
 
 
 def test_kernel_reaches_fci():

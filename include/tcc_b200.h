@@ -63,6 +63,11 @@ int64_t tcc_civector_size(const tcc_plan* plan);  /* ucc.py:1282-1290 */
 int64_t tcc_num_strings(const tcc_plan* plan);    /* per-spin strings (hcb: all strings) */
 int tcc_num_ops(const tcc_plan* plan);
 int tcc_num_params(const tcc_plan* plan);         /* max(param_ids)+1, ucc.py:1266-1271 */
+/* the batch schedule: runs of excitations (after provably commuting swaps) applied by one launch each */
+int tcc_num_batches(const tcc_plan* plan);
+int tcc_batch_info(const tcc_plan* plan, int b, int32_t* n_ops, int32_t* active_alpha, int32_t* active_beta,
+                   int32_t* n_tiles, int32_t* max_tile_rows, int32_t* max_tile_cols,
+                   int32_t* op_indices /* [n_ops of the batch] or NULL */);
 /* bytes of device memory held by the plan's tables / workspaces */
 int64_t tcc_plan_device_bytes(const tcc_plan* plan);
 
@@ -74,6 +79,10 @@ int tcc_ci_strings_spin(const tcc_plan* plan, uint64_t* out_host /* [num_strings
  * compact per-spin lists: partner address, G matrix element (fket_phase), diag of G^2 */
 int tcc_excitation_tables(const tcc_plan* plan, int j, uint64_t* perm_host, int8_t* phase_host,
                           int8_t* f2_host);
+/* the engine's internal string order: ref2int[r] = storage address of the string whose reference
+ * address (ci_utils.py:22 order) is r.  Vectors crossing this ABI are ALWAYS in reference order,
+ * except for the storage-order building blocks below. */
+int tcc_storage_order(const tcc_plan* plan, uint32_t* ref2int_host /* [num_strings] */);
 
 /* ---- Hamiltonian -------------------------------------------------------------------------
  * Replaces get_h_fcifunc_from_integral (hamiltonian.py:146-155; pyscf absorb_h1e with fac 0.5)
@@ -111,7 +120,10 @@ int tcc_energy_and_grad_host(tcc_plan* plan, const double* params_host, const do
 int tcc_apply_excitation_host(tcc_plan* plan, const double* c_host, const int32_t* ex_op,
                               int ex_op_len, double* out_host);
 
-/* ---- building blocks (used by the sharded multi-GPU driver and the benchmarks) ------------ */
+/* ---- building blocks (used by the sharded multi-GPU driver and the benchmarks).  These operate
+ * on vectors in the engine's STORAGE order; convert with the two calls below. --------------- */
+int tcc_to_storage_order(tcc_plan* plan, const double* ref_dev, double* storage_dev, void* stream);
+int tcc_from_storage_order(tcc_plan* plan, const double* storage_dev, double* ref_dev, void* stream);
 /* one UCC factor exp(theta G_j) applied in place to a device vector */
 int tcc_rotate(tcc_plan* plan, int j, double theta, double* c_dev, void* stream);
 /* reverse-sweep step for excitation j: ket,bra <- exp(-theta G_j); *grad_dev = <bra|G_j|ket> (overwritten) */
@@ -135,9 +147,14 @@ int64_t tcc_launch_count(const tcc_plan* plan);
 #define TCC_PROF_SIGMA_SS 6
 #define TCC_PROF_SIGMA_AB 7
 #define TCC_PROF_DOT 8
-#define TCC_PROF_SLOTS 9
+#define TCC_PROF_FWD_BATCH 9  /* batched forward sweep: 16 N bytes per launch (whole vector read + written) */
+#define TCC_PROF_REV_BATCH 10 /* batched reverse sweep: 32 N bytes per launch pair (ket and bra) */
+#define TCC_PROF_SLOTS 11
 int tcc_profile_enable(tcc_plan* plan, int on); /* also resets the accumulators */
 int tcc_profile_read(tcc_plan* plan, double* ms /*[TCC_PROF_SLOTS]*/, int64_t* launches, int64_t* bytes);
+/* per-batch device time of the last tcc_energy_and_grad call (forward launch, reverse launch pair), in ms;
+ * `on` (de)activates the recording for the following calls; fwd_ms / rev_ms [tcc_num_batches] may be NULL */
+int tcc_profile_batches(tcc_plan* plan, int on, float* fwd_ms, float* rev_ms);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,11 @@ SIGNATURES = {
     "tcc_num_ops": (C.c_int, [_p]),
     "tcc_num_params": (C.c_int, [_p]),
     "tcc_plan_device_bytes": (C.c_int64, [_p]),
+    "tcc_num_batches": (C.c_int, [_p]),
+    "tcc_batch_info": (C.c_int, [_p, C.c_int] + [_ip] * 7),
+    "tcc_storage_order": (C.c_int, [_p, C.POINTER(C.c_uint32)]),
+    "tcc_to_storage_order": (C.c_int, [_p, _p, _p, _p]),
+    "tcc_from_storage_order": (C.c_int, [_p, _p, _p, _p]),
     "tcc_ci_strings_spin": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "tcc_excitation_tables": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int8), C.POINTER(C.c_int8)]),
     "tcc_set_hamiltonian": (C.c_int, [_p, _dp, _dp]),
@@ -53,9 +58,10 @@ SIGNATURES = {
     "tcc_launch_count": (C.c_int64, [_p]),
     "tcc_profile_enable": (C.c_int, [_p, C.c_int]),
     "tcc_profile_read": (C.c_int, [_p, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "tcc_profile_batches": (C.c_int, [_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
 
-PROF_SLOTS = ("fwd_beta", "fwd_alpha", "fwd_alphabeta", "rev_beta", "rev_alpha", "rev_alphabeta", "sigma_ss", "sigma_ab", "dot")
+PROF_SLOTS = ("fwd_beta", "fwd_alpha", "fwd_alphabeta", "rev_beta", "rev_alpha", "rev_alphabeta", "sigma_ss", "sigma_ab", "dot", "fwd_batch", "rev_batch")
 
 _lib = None
 

@@ -1,0 +1,369 @@
+// Batched excitation kernels: one launch applies a whole batch of UCC factors to every closed tile of the
+// CI matrix, so the vector crosses HBM once per batch instead of once per excitation
+// (tencirchem/static/evolve_civector.py:165-177 forward sweep, :221-243 reverse sweep).
+//
+// CTA = one tile = (panel of alpha classes) x (panel of beta classes), see plan.hpp.  The tile is gathered
+// into shared memory (rows by warp, columns in ascending address order so the global accesses coalesce),
+// all excitations of the batch are applied in order with a barrier between them, and the tile is written
+// back.  The reverse-sweep variant holds the ket and the bra tile and accumulates <bra|G_j|ket> per
+// excitation; per-tile partial sums go to a [n_ops, n_tiles] buffer that a second kernel reduces in a fixed
+// order (deterministic gradients).
+#include "batch_kernels.cuh"
+
+namespace tcc {
+
+constexpr int BK_THREADS = 256;
+constexpr int BK_WARPS = BK_THREADS / 32;
+constexpr int BK_DEPTH = 4;  // excitations per prefetch group
+constexpr int BK_COLCH = 4;  // tile columns per lane kept in registers (tiles up to 128 columns)
+
+// per-op record resolved for the tile's (e_alpha, e_beta) at kernel start
+struct SmemOp {
+    int off, cnt;   // slice of the expanded pair list
+    double cs, sn;  // cos, sin * s0 * (spectator sign of this tile)
+    double gs;      // spectator sign of this tile: multiplies the tile's gradient partial
+};
+
+// One rotation pass over the expanded pair list of an excitation inside the tile.  REP: the tile has a side
+// without active orbitals whose `n_rep` rows (or columns) all get the same pair list, `stride` apart.
+template <int NV, bool REP>
+__device__ __forceinline__ double rotate_pairs(double* __restrict__ t0, double* __restrict__ t1, const SmemOp& op,
+                                               const uint32_t* __restrict__ plist, int n_rep, int stride, int tid, int nthreads) {
+    double acc = 0.0;
+    const int cnt = op.cnt;
+    const int total = REP ? cnt * n_rep : cnt;
+    if (tid >= total) return acc;
+    const double cs = op.cs, sn = op.sn;
+    const uint32_t* lp = plist + op.off;
+    int k = tid, base = 0, q = 0, r = 0;
+    if (REP) {
+        q = nthreads / cnt;
+        r = nthreads - q * cnt;
+        const int rep = tid / cnt;
+        k = tid - rep * cnt;
+        base = rep * stride;
+        q *= stride;
+    }
+    for (int idx = tid; idx < total; idx += nthreads) {
+        const uint32_t e = __ldg(lp + k);
+        const int i1 = base + int(e & 0x7fffu), i2 = base + int((e >> 15) & 0x7fffu);
+        const bool neg = (e >> 30) & 1u;
+        const double p = neg ? -sn : sn;
+        const double x = t0[i1], y = t0[i2];
+        const double nx = cs * x + p * y, ny = cs * y - p * x;
+        t0[i1] = nx;
+        t0[i2] = ny;
+        if (NV == 2) {
+            const double bx = t1[i1], by = t1[i2];
+            const double nbx = cs * bx + p * by, nby = cs * by - p * bx;
+            t1[i1] = nbx;
+            t1[i2] = nby;
+            // t0 = ket, t1 = bra: bra_I (G ket)_I + bra_J (G ket)_J = +-(bra_I ket_J - bra_J ket_I)
+            const double g = nbx * ny - nby * nx;
+            acc += neg ? -g : g;
+        }
+        if (REP) {
+            k += r;
+            base += q;
+            if (k >= cnt) {
+                k -= cnt;
+                base += stride;
+            }
+        } else {
+            k += nthreads;
+        }
+    }
+    return acc;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(BK_THREADS)
+batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, BatchDev bd, const double2* __restrict__ rot,
+             double* __restrict__ partials, int n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tile_id = blockIdx.x;
+    const int pa_id = tile_id / bd.B.n_panels;
+    const PanelDesc pa = bd.A.panels[pa_id];
+    const PanelDesc pb = bd.B.panels[tile_id - pa_id * bd.B.n_panels];
+    // an active side has one class per panel (G == 1); a side without active orbitals packs G single-string
+    // classes, none of which is ever paired
+    const int nR = int(pa.G) * int(pa.c), nC = int(pb.G) * int(pb.c);
+    const int ld = bd.B.m > 0 ? (nC | 1) : bd.ld_fixed;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    double* t0 = reinterpret_cast<double*>(smem_raw);
+    double* t1 = t0 + (NV == 2 ? size_t(nR) * ld : 0);
+    SmemOp* sops = reinterpret_cast<SmemOp*>(t1 + size_t(nR) * ld);
+    double* wpart = reinterpret_cast<double*>(sops + bd.nops);  // [nops][nwarps] (NV == 2)
+    uint32_t* row_addr = reinterpret_cast<uint32_t*>(wpart + (NV == 2 ? size_t(bd.nops) * nwarps : 0));  // [nR]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t* addr_a = bd.A.addr + pa.off;
+    const uint32_t* cols_sorted = bd.B.addr_sorted + pb.off;
+    const uint16_t* ord_b = bd.B.ord + pb.off;
+    for (int i = tid; i < nR; i += nthreads) row_addr[i] = __ldg(addr_a + i);
+    // each lane owns up to BK_COLCH columns of the tile (ascending global address => coalesced accesses)
+    int64_t colg[BK_COLCH];
+    int lcs[BK_COLCH];
+    const bool reg_cols = nC <= 32 * BK_COLCH;
+#pragma unroll
+    for (int j = 0; j < BK_COLCH; ++j) {
+        const int t = lane + 32 * j;
+        colg[j] = 0;
+        lcs[j] = -1;
+        if (reg_cols && t < nC) {
+            colg[j] = __ldg(cols_sorted + t);
+            lcs[j] = __ldg(ord_b + t);
+        }
+    }
+
+    const uint32_t sig_a = bd.A.sigma[pa.class_off];
+    const uint32_t sig_b = bd.B.sigma[pb.class_off];
+    for (int t = tid; t < bd.nops; t += nthreads) {
+        const BatchOp op = bd.ops[t];
+        const int fwd_pos = bd.reversed ? bd.nops - 1 - t : t;
+        const int* pi = bd.plist_index + ((size_t(fwd_pos) * (bd.A.m + 1) + int(pa.e)) * (bd.B.m + 1) + int(pb.e)) * 2;
+        SmemOp so;
+        so.off = pi[0];
+        so.cnt = pi[1];
+        uint32_t sign = 0;
+        if (op.h_a >= 0) sign ^= uint32_t(__popc(sig_a & op.zspec_a));
+        if (op.h_b >= 0) sign ^= uint32_t(__popc(sig_b & op.zspec_b));
+        const double2 cs = __ldg(rot + op.op_index);
+        so.cs = cs.x;
+        so.sn = (sign & 1u) ? -cs.y : cs.y;
+        so.gs = (sign & 1u) ? -1.0 : 1.0;
+        sops[t] = so;
+    }
+
+    __syncthreads();  // row_addr, sops
+    // ---- gather the tile
+    if (reg_cols) {
+        for (int lr = warp; lr < nR; lr += nwarps) {
+            const double* src0 = v0 + int64_t(row_addr[lr]) * nb;
+            const double* src1 = NV == 2 ? v1 + int64_t(row_addr[lr]) * nb : nullptr;
+            double a[BK_COLCH], b[BK_COLCH];
+#pragma unroll
+            for (int j = 0; j < BK_COLCH; ++j)
+                if (lcs[j] >= 0) {
+                    a[j] = src0[colg[j]];
+                    if (NV == 2) b[j] = src1[colg[j]];
+                }
+#pragma unroll
+            for (int j = 0; j < BK_COLCH; ++j)
+                if (lcs[j] >= 0) {
+                    t0[lr * ld + lcs[j]] = a[j];
+                    if (NV == 2) t1[lr * ld + lcs[j]] = b[j];
+                }
+        }
+    } else {
+        for (int lr = warp; lr < nR; lr += nwarps) {
+            const int64_t row = int64_t(row_addr[lr]) * nb;
+            for (int t = lane; t < nC; t += 32) {
+                const int lc = __ldg(ord_b + t);
+                const int64_t g = row + __ldg(cols_sorted + t);
+                t0[lr * ld + lc] = v0[g];
+                if (NV == 2) t1[lr * ld + lc] = v1[g];
+            }
+        }
+    }
+    __syncthreads();
+
+    const bool rep_a = bd.A.m == 0 && nR > 1, rep_b = bd.B.m == 0 && nC > 1;
+    if (rep_a || rep_b) {
+        // a side without active orbitals: the same pair list for each of its rows / columns (rare: one-sided
+        // batches); not software-pipelined
+        for (int t = 0; t < bd.nops; ++t) {
+            const SmemOp& op = sops[t];
+            double acc = rep_a ? rotate_pairs<NV, true>(t0, t1, op, bd.plist, nR, ld, tid, nthreads)
+                               : rotate_pairs<NV, true>(t0, t1, op, bd.plist, nC, 1, tid, nthreads);
+            if (NV == 2) {
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+                if (lane == 0) wpart[t * nwarps + warp] = acc;
+            }
+            __syncthreads();
+        }
+    } else {
+        // Software pipeline: the pair-list entries do not depend on the data, so the entries of the NEXT group of
+        // BK_DEPTH excitations are fetched (L2 latency) while the current group is applied; only shared-memory and
+        // FP64 latency stays on the barrier-to-barrier critical path.
+        const uint32_t* __restrict__ plist = bd.plist;
+        uint32_t cur0[BK_DEPTH], cur1[BK_DEPTH], nxt0[BK_DEPTH], nxt1[BK_DEPTH];
+        double accs[BK_DEPTH];
+        auto fetch = [&](int tbase, uint32_t* e0, uint32_t* e1) {
+#pragma unroll
+            for (int j = 0; j < BK_DEPTH; ++j) {
+                const int t = tbase + j;
+                e0[j] = 0;
+                e1[j] = 0;
+                if (t < bd.nops) {
+                    const int off = sops[t].off, cnt = sops[t].cnt;
+                    if (tid < cnt) e0[j] = __ldg(plist + off + tid);
+                    if (tid + nthreads < cnt) e1[j] = __ldg(plist + off + tid + nthreads);
+                }
+            }
+        };
+        auto rotate_one = [&](uint32_t e, double cs, double sn, double& acc) {
+            const int i1 = int(e & 0x7fffu), i2 = int((e >> 15) & 0x7fffu);
+            const bool neg = (e >> 30) & 1u;
+            const double p = neg ? -sn : sn;
+            const double x = t0[i1], y = t0[i2];
+            const double nx = cs * x + p * y, ny = cs * y - p * x;
+            t0[i1] = nx;
+            t0[i2] = ny;
+            if (NV == 2) {
+                const double bx = t1[i1], by = t1[i2];
+                const double nbx = cs * bx + p * by, nby = cs * by - p * bx;
+                t1[i1] = nbx;
+                t1[i2] = nby;
+                const double g = nbx * ny - nby * nx;
+                acc += neg ? -g : g;
+            }
+        };
+        fetch(0, cur0, cur1);
+        int cnt_n = bd.nops > 0 ? sops[0].cnt : 0;
+        int off_n = bd.nops > 0 ? sops[0].off : 0;
+        double cs_n = bd.nops > 0 ? sops[0].cs : 0.0, sn_n = bd.nops > 0 ? sops[0].sn : 0.0;
+        for (int tb = 0; tb < bd.nops; tb += BK_DEPTH) {
+            fetch(tb + BK_DEPTH, nxt0, nxt1);
+#pragma unroll
+            for (int j = 0; j < BK_DEPTH; ++j) {
+                const int t = tb + j;
+                if (t < bd.nops) {
+                    const int cnt = cnt_n, off = off_n;
+                    const double cs = cs_n, sn = sn_n;
+                    if (t + 1 < bd.nops) {  // next record read before this excitation's barrier
+                        cnt_n = sops[t + 1].cnt;
+                        off_n = sops[t + 1].off;
+                        cs_n = sops[t + 1].cs;
+                        sn_n = sops[t + 1].sn;
+                    }
+                    double acc = 0.0;
+                    if (tid < cnt) rotate_one(cur0[j], cs, sn, acc);
+                    if (tid + nthreads < cnt) rotate_one(cur1[j], cs, sn, acc);
+                    for (int idx = tid + 2 * nthreads; idx < cnt; idx += nthreads) rotate_one(__ldg(plist + off + idx), cs, sn, acc);
+                    accs[j] = acc;
+                    __syncthreads();
+                } else {
+                    accs[j] = 0.0;
+                }
+            }
+            if (NV == 2) {
+                // the BK_DEPTH warp reductions of the group run interleaved, off the barrier-to-barrier path
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < BK_DEPTH; ++j) accs[j] += __shfl_down_sync(0xffffffffu, accs[j], o);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < BK_DEPTH; ++j)
+                        if (tb + j < bd.nops) wpart[(tb + j) * nwarps + warp] = accs[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < BK_DEPTH; ++j) {
+                cur0[j] = nxt0[j];
+                cur1[j] = nxt1[j];
+            }
+        }
+    }
+
+    // ---- scatter the tile back
+    if (reg_cols) {
+        for (int lr = warp; lr < nR; lr += nwarps) {
+            double* dst0 = v0 + int64_t(row_addr[lr]) * nb;
+            double* dst1 = NV == 2 ? v1 + int64_t(row_addr[lr]) * nb : nullptr;
+#pragma unroll
+            for (int j = 0; j < BK_COLCH; ++j)
+                if (lcs[j] >= 0) {
+                    dst0[colg[j]] = t0[lr * ld + lcs[j]];
+                    if (NV == 2) dst1[colg[j]] = t1[lr * ld + lcs[j]];
+                }
+        }
+    } else {
+        for (int lr = warp; lr < nR; lr += nwarps) {
+            const int64_t row = int64_t(row_addr[lr]) * nb;
+            for (int t = lane; t < nC; t += 32) {
+                const int lc = __ldg(ord_b + t);
+                const int64_t g = row + __ldg(cols_sorted + t);
+                v0[g] = t0[lr * ld + lc];
+                if (NV == 2) v1[g] = t1[lr * ld + lc];
+            }
+        }
+    }
+    if (NV == 2) {
+        __syncthreads();
+        for (int t = tid; t < bd.nops; t += nthreads) {
+            double s = 0.0;
+            for (int w = 0; w < nwarps; ++w) s += wpart[t * nwarps + w];
+            partials[int64_t(t) * n_tiles + tile_id] = s * sops[t].gs;
+        }
+    }
+}
+
+// grad_ops[op_index] = s0 * sum over tiles of partials[t, :], fixed order
+__global__ void __launch_bounds__(256) batch_grad_reduce_kernel(const double* __restrict__ partials, int n_tiles,
+                                                                const BatchOp* __restrict__ ops, double* __restrict__ grad_ops) {
+    __shared__ double wsum[8];
+    const int t = blockIdx.x;
+    const double* row = partials + int64_t(t) * n_tiles;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_tiles; i += 256) s += row[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += wsum[w];
+        grad_ops[ops[t].op_index] = tot * double(ops[t].s0);
+    }
+}
+
+size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv) {
+    size_t ld = size_t(max_cols) | 1;
+    size_t bytes = size_t(nv) * max_rows * ld * sizeof(double);
+    bytes += size_t(nops) * sizeof(SmemOp);
+    if (nv == 2) bytes += size_t(nops) * BK_WARPS * sizeof(double);
+    bytes += size_t(max_rows) * sizeof(uint32_t);
+    return bytes + 16;
+}
+
+cudaError_t batch_kernels_configure() {
+    cudaError_t e = cudaFuncSetAttribute(batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+}
+
+void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem, int threads,
+                          cudaStream_t st) {
+    dim3 grid(unsigned(bd.B.n_panels) * unsigned(bd.A.n_panels), 1, 1);
+    batch_kernel<1><<<grid, threads, smem, st>>>(v, nullptr, nb, bd, rot, nullptr, 0);
+}
+
+void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem,
+                          int threads, double* partials, double* grad_ops, cudaStream_t st) {
+    dim3 grid(unsigned(bd.B.n_panels) * unsigned(bd.A.n_panels), 1, 1);
+    const int n_tiles = bd.B.n_panels * bd.A.n_panels;
+    batch_kernel<2><<<grid, threads, smem, st>>>(ket, bra, nb, bd, rot, partials, n_tiles);
+    batch_grad_reduce_kernel<<<bd.nops, 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops);
+}
+
+// out[a, b] = in[map_a[a], map_b[b]]  (storage order <-> reference order)
+__global__ void __launch_bounds__(256) permute_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t na, int64_t nb,
+                                                      const uint32_t* __restrict__ map_a, const uint32_t* __restrict__ map_b) {
+    const int64_t a = blockIdx.y;
+    const int64_t src_row = (map_a ? int64_t(map_a[a]) : a) * nb;
+    for (int64_t b = int64_t(blockIdx.x) * 256 + threadIdx.x; b < nb; b += int64_t(gridDim.x) * 256)
+        out[a * nb + b] = in[src_row + map_b[b]];
+}
+
+void launch_permute(const double* in, double* out, int64_t na, int64_t nb, const uint32_t* map_a, const uint32_t* map_b,
+                    cudaStream_t st) {
+    unsigned gx = unsigned(std::min<int64_t>((nb + 255) / 256, 64));
+    for (int64_t r0 = 0; r0 < na; r0 += 65535) {
+        unsigned gy = unsigned(std::min<int64_t>(na - r0, 65535));
+        permute_kernel<<<dim3(gx, gy, 1), 256, 0, st>>>(in, out + r0 * nb, gy, nb, map_a ? map_a + r0 : nullptr, map_b);
+    }
+}
+
+}  // namespace tcc

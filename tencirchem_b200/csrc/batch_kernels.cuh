@@ -1,0 +1,43 @@
+// Device-side descriptors and launchers of the batched excitation kernels (batch_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "plan.hpp"
+
+namespace tcc {
+
+struct SideDev {
+    const uint32_t* addr;
+    const uint16_t* ord;
+    const uint32_t* addr_sorted;
+    const uint32_t* sigma;
+    const PanelDesc* panels;
+    const uint32_t* tab;
+    const int32_t* tab_index;
+    int m;
+    int n_panels;
+};
+
+struct BatchDev {
+    SideDev A, B;
+    const BatchOp* ops;  // application order for this direction
+    const uint32_t* plist;
+    const int32_t* plist_index;  // indexed by the FORWARD position of the op in the batch
+    int nops;
+    int ld_fixed;
+    int reversed;  // ops[] is the forward list reversed
+};
+
+cudaError_t batch_kernels_configure();
+size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv);
+void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem, int threads,
+                          cudaStream_t st);
+void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem,
+                          int threads, double* partials, double* grad_ops, cudaStream_t st);
+void launch_permute(const double* in, double* out, int64_t na, int64_t nb, const uint32_t* map_a, const uint32_t* map_b,
+                    cudaStream_t st);
+
+}  // namespace tcc

@@ -10,11 +10,13 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/tcc_b200.h"
+#include "batch_kernels.cuh"
 #include "kernels.cuh"
 #include "plan.hpp"
 
@@ -94,20 +96,60 @@ struct Profiler {
     }
 };
 
+struct BatchDevSet {
+    BatchDev fwd, rev;
+    size_t smem_fwd = 0, smem_rev = 0;
+    int n_tiles = 0;
+    int nops = 0;
+    int max_rows = 0, max_cols = 0;
+    std::vector<void*> allocs;
+};
+
+struct BatchTimer {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;  // fwd: [0 .. nb], rev: [nb+1 .. 2nb+1]
+    std::vector<float> fwd_ms, rev_ms;
+    void ensure(size_t nb) {
+        while (ev.size() < 2 * nb + 2) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev.push_back(e);
+        }
+        fwd_ms.assign(nb, 0.f);
+        rev_ms.assign(nb, 0.f);
+    }
+    ~BatchTimer() {
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+};
+
 struct tcc_plan {
     HostPlan hp;
     Profiler prof;
+    BatchTimer btimer;
     int device = 0;
+    int mode = 0;  // 0 = batched tiles, 1 = one launch per excitation
+    int batch_threads = 128;
     std::vector<DevHop> dhops;
+    std::vector<BatchDevSet> dbatches;
     double* ket = nullptr;
     double* bra = nullptr;
     double* ws1 = nullptr;
     double* ws2 = nullptr;
+    double* io1 = nullptr;  // reference-order staging for the host-buffer entry points
+    double* io2 = nullptr;
     double* partials = nullptr;
     unsigned* ticket = nullptr;
-    double* grad_ops = nullptr;  // [n_ops] on the device
-    double* scalars = nullptr;   // small device scratch
+    double* grad_ops = nullptr;  // [n_ops + 8] on the device
+    double* bpart = nullptr;     // per-tile gradient partials of the batched reverse sweep
     double* pinned = nullptr;    // pinned host staging [n_ops + 8]
+    double2* d_rot_fwd = nullptr;  // [n_ops] (cos, sin * s0)
+    double2* d_rot_rev = nullptr;  // [n_ops] (cos, -sin * s0)
+    double2* h_rot = nullptr;      // pinned [2 * n_ops]
+    cudaEvent_t rot_event = nullptr;
+    uint32_t* d_ref2int = nullptr;
+    uint32_t* d_int2ref = nullptr;
+    int64_t hf_index = 0;
     bool has_h = false;
     Link* d_links = nullptr;
     double* d_w = nullptr;
@@ -119,6 +161,7 @@ struct tcc_plan {
     double* d_hop = nullptr;
     double* d_diag2 = nullptr;
     int64_t* d_binom = nullptr;
+    int* d_bitpos = nullptr;
     int64_t launches = 0;
     int64_t dev_bytes = 0;
 };
@@ -127,6 +170,17 @@ template <typename T>
 static cudaError_t dev_alloc(tcc_plan* p, T** ptr, size_t count) {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(ptr), count * sizeof(T) + 16);
     if (e == cudaSuccess) p->dev_bytes += int64_t(count * sizeof(T));
+    return e;
+}
+
+template <typename T>
+static cudaError_t dev_upload(tcc_plan* p, const std::vector<T>& h, const T** out, std::vector<void*>* owner) {
+    T* d = nullptr;
+    cudaError_t e = dev_alloc(p, &d, h.size() ? h.size() : 1);
+    if (e != cudaSuccess) return e;
+    owner->push_back(d);
+    if (!h.empty()) e = cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = d;
     return e;
 }
 
@@ -143,6 +197,52 @@ static int upload_hop(tcc_plan* p, int id) {
         CUDA_TRY(cudaMemcpy(d.src, h.src.data(), d.len * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d.dst, h.dst.data(), d.len * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
+    return 0;
+}
+
+static int upload_side(tcc_plan* p, const SideBatch& s, SideDev* d, std::vector<void*>* owner) {
+    CUDA_TRY(dev_upload(p, s.addr, &d->addr, owner));
+    CUDA_TRY(dev_upload(p, s.ord, &d->ord, owner));
+    CUDA_TRY(dev_upload(p, s.addr_sorted, &d->addr_sorted, owner));
+    CUDA_TRY(dev_upload(p, s.sigma, &d->sigma, owner));
+    CUDA_TRY(dev_upload(p, s.panels, &d->panels, owner));
+    CUDA_TRY(dev_upload(p, s.tab, &d->tab, owner));
+    CUDA_TRY(dev_upload(p, s.tab_index, &d->tab_index, owner));
+    d->m = s.m;
+    d->n_panels = int(s.panels.size());
+    return 0;
+}
+
+static int upload_batches(tcc_plan* p) {
+    HostPlan& hp = p->hp;
+    p->dbatches.resize(hp.batches.size());
+    size_t max_part = 1;
+    for (size_t b = 0; b < hp.batches.size(); ++b) {
+        const Batch& hb = hp.batches[b];
+        BatchDevSet& db = p->dbatches[b];
+        if (int rc = upload_side(p, hb.A, &db.fwd.A, &db.allocs)) return rc;
+        if (int rc = upload_side(p, hb.B, &db.fwd.B, &db.allocs)) return rc;
+        CUDA_TRY(dev_upload(p, hb.plist, &db.fwd.plist, &db.allocs));
+        CUDA_TRY(dev_upload(p, hb.plist_index, &db.fwd.plist_index, &db.allocs));
+        db.fwd.ld_fixed = hb.ld_fixed;
+        db.fwd.reversed = 0;
+        db.rev = db.fwd;
+        db.rev.reversed = 1;
+        std::vector<BatchOp> rev_ops(hb.ops.rbegin(), hb.ops.rend());
+        CUDA_TRY(dev_upload(p, hb.ops, &db.fwd.ops, &db.allocs));
+        CUDA_TRY(dev_upload(p, rev_ops, &db.rev.ops, &db.allocs));
+        db.nops = db.fwd.nops = db.rev.nops = int(hb.ops.size());
+        db.n_tiles = db.fwd.A.n_panels * db.fwd.B.n_panels;
+        db.max_rows = hb.A.max_panel;
+        db.max_cols = hb.B.max_panel;
+        db.smem_fwd = batch_smem_bytes(hb.A.max_panel, hb.B.max_panel, db.nops, 1);
+        db.smem_rev = batch_smem_bytes(hb.A.max_panel, hb.B.max_panel, db.nops, 2);
+        if (db.smem_rev > 232448)
+            return fail(TCC_ERR_BAD_ARGUMENT, "batch tile does not fit in shared memory: lower TCC_B200_TILE_ELEMS");
+        max_part = std::max(max_part, size_t(db.nops) * size_t(db.n_tiles));
+    }
+    CUDA_TRY(dev_alloc(p, &p->bpart, max_part));
+    CUDA_TRY(batch_kernels_configure());
     return 0;
 }
 
@@ -170,10 +270,35 @@ static int use_device(const tcc_plan* p) {
     return 0;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// reference order -> storage order and back (vectors crossing the ABI are in reference order)
+static void to_storage(tcc_plan* p, const double* ref, double* st_vec, cudaStream_t st) {
+    const HostPlan& hp = p->hp;
+    if (hp.identity_layout) {
+        if (ref != st_vec) cudaMemcpyAsync(st_vec, ref, hp.N * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        return;
+    }
+    launch_permute(ref, st_vec, hp.na, hp.nb, hp.hcb ? nullptr : p->d_int2ref, p->d_int2ref, st);
+    p->launches += 1;
+}
+static void from_storage(tcc_plan* p, const double* st_vec, double* ref, cudaStream_t st) {
+    const HostPlan& hp = p->hp;
+    if (hp.identity_layout) {
+        if (ref != st_vec) cudaMemcpyAsync(ref, st_vec, hp.N * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        return;
+    }
+    launch_permute(st_vec, ref, hp.na, hp.nb, hp.hcb ? nullptr : p->d_ref2int, p->d_ref2int, st);
+    p->launches += 1;
+}
+
 extern "C" {
 
 const char* tcc_last_error(void) { return g_error.c_str(); }
-const char* tcc_version(void) { return "tencirchem_b200 0.1 (sm_100a)"; }
+const char* tcc_version(void) { return "tencirchem_b200 0.2 (sm_100a)"; }
 
 int tcc_device_count(void) {
     int n = 0;
@@ -207,7 +332,7 @@ int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t*
             delete p;
             return fail(TCC_ERR_BAD_EXCITATION, "Excitation of length " + std::to_string(len) + " not supported");
         }
-        rc = p->hp.make_op(ex_ops_flat + off, len, pid, &p->hp.ops[j]);
+        rc = p->hp.parse_op(ex_ops_flat + off, len, pid, &p->hp.ops[j]);
         if (rc) {
             g_error = p->hp.error;
             delete p;
@@ -217,6 +342,14 @@ int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t*
         if (pid > max_param) max_param = pid;
     }
     p->hp.n_params = max_param + 1;
+    p->mode = env_int("TCC_B200_PER_OP", 0) ? 1 : 0;
+    p->batch_threads = std::min(256, std::max(32, env_int("TCC_B200_BATCH_THREADS", 128) / 32 * 32));
+    p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0);
+    {
+        uint32_t hf = p->hp.k ? ((1u << p->hp.k) - 1) : 0u;
+        int64_t r = p->hp.rank(hf);
+        p->hf_index = (p->hp.hcb ? 0 : r * p->hp.nb) + r;
+    }
     if (device == -1) {  // host-only plan: strings / tables introspection, no compute
         p->device = -1;
         *out = p;
@@ -240,16 +373,25 @@ int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t*
     if (int rc_dev = use_device(p)) return bail(rc_dev);
     for (size_t h = 0; h < p->hp.hops.size(); ++h)
         if (upload_hop(p, int(h))) return bail(TCC_ERR_CUDA);
+    if (int rc2 = upload_batches(p)) return bail(rc2);
     if (cudaMalloc(&p->partials, sizeof(double) * reverse_partials_capacity()) != cudaSuccess ||
         cudaMalloc(&p->ticket, sizeof(unsigned)) != cudaSuccess ||
         cudaMalloc(&p->grad_ops, sizeof(double) * (n_ops + 8)) != cudaSuccess ||
-        cudaMalloc(&p->scalars, sizeof(double) * 8) != cudaSuccess ||
-        cudaMallocHost(&p->pinned, sizeof(double) * (n_ops + 8)) != cudaSuccess) {
+        cudaMalloc(&p->d_rot_fwd, sizeof(double2) * (n_ops + 1)) != cudaSuccess ||
+        cudaMalloc(&p->d_rot_rev, sizeof(double2) * (n_ops + 1)) != cudaSuccess ||
+        cudaMalloc(&p->d_ref2int, sizeof(uint32_t) * p->hp.nstr) != cudaSuccess ||
+        cudaMalloc(&p->d_int2ref, sizeof(uint32_t) * p->hp.nstr) != cudaSuccess ||
+        cudaMallocHost(&p->h_rot, sizeof(double2) * (2 * n_ops + 2)) != cudaSuccess ||
+        cudaMallocHost(&p->pinned, sizeof(double) * (n_ops + 8)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->rot_event, cudaEventDisableTiming) != cudaSuccess) {
         g_error = std::string("plan workspace allocation: ") + cudaGetErrorString(cudaGetLastError());
         return bail(TCC_ERR_CUDA);
     }
+    cudaMemcpy(p->d_ref2int, p->hp.ref2int.data(), sizeof(uint32_t) * p->hp.nstr, cudaMemcpyHostToDevice);
+    cudaMemcpy(p->d_int2ref, p->hp.int2ref.data(), sizeof(uint32_t) * p->hp.nstr, cudaMemcpyHostToDevice);
     cudaMemset(p->ticket, 0, sizeof(unsigned));
     cudaMemset(p->grad_ops, 0, sizeof(double) * (n_ops + 8));
+    cudaEventRecord(p->rot_event, nullptr);
     *out = p;
     return 0;
 }
@@ -261,19 +403,30 @@ void tcc_plan_destroy(tcc_plan* p) {
         return;
     }
     cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
     for (auto& d : p->dhops) {
         cudaFree(d.src);
         cudaFree(d.dst);
     }
+    for (auto& b : p->dbatches)
+        for (void* q : b.allocs) cudaFree(q);
     cudaFree(p->ket);
     cudaFree(p->bra);
     cudaFree(p->ws1);
     cudaFree(p->ws2);
+    cudaFree(p->io1);
+    cudaFree(p->io2);
     cudaFree(p->partials);
     cudaFree(p->ticket);
     cudaFree(p->grad_ops);
-    cudaFree(p->scalars);
+    cudaFree(p->bpart);
+    cudaFree(p->d_rot_fwd);
+    cudaFree(p->d_rot_rev);
+    cudaFree(p->d_ref2int);
+    cudaFree(p->d_int2ref);
+    if (p->h_rot) cudaFreeHost(p->h_rot);
     if (p->pinned) cudaFreeHost(p->pinned);
+    if (p->rot_event) cudaEventDestroy(p->rot_event);
     cudaFree(p->d_links);
     cudaFree(p->d_w);
     cudaFree(p->d_ell_col);
@@ -283,6 +436,7 @@ void tcc_plan_destroy(tcc_plan* p) {
     cudaFree(p->d_hop);
     cudaFree(p->d_diag2);
     cudaFree(p->d_binom);
+    cudaFree(p->d_bitpos);
     delete p;
 }
 
@@ -290,6 +444,7 @@ int64_t tcc_civector_size(const tcc_plan* p) { return p ? p->hp.N : 0; }
 int64_t tcc_num_strings(const tcc_plan* p) { return p ? p->hp.nstr : 0; }
 int tcc_num_ops(const tcc_plan* p) { return p ? int(p->hp.ops.size()) : 0; }
 int tcc_num_params(const tcc_plan* p) { return p ? p->hp.n_params : 0; }
+int tcc_num_batches(const tcc_plan* p) { return p ? int(p->hp.batches.size()) : 0; }
 int64_t tcc_plan_device_bytes(const tcc_plan* p) { return p ? p->dev_bytes : 0; }
 int64_t tcc_launch_count(const tcc_plan* p) { return p ? p->launches : 0; }
 
@@ -298,9 +453,30 @@ int64_t tcc_op_support_bytes(const tcc_plan* p, int j) {
     return 32 * p->hp.support_pairs(p->hp.ops[j]);  // 2 elements per pair, each read and written once (8 B)
 }
 
+int tcc_batch_info(const tcc_plan* p, int b, int32_t* n_ops, int32_t* active_alpha, int32_t* active_beta, int32_t* n_tiles,
+                   int32_t* max_tile_rows, int32_t* max_tile_cols, int32_t* op_indices /* [n_ops of the batch] or NULL */) {
+    if (!p || b < 0 || b >= int(p->hp.batches.size())) return fail(TCC_ERR_BAD_ARGUMENT, "batch index out of range");
+    const Batch& hb = p->hp.batches[b];
+    if (n_ops) *n_ops = int32_t(hb.ops.size());
+    if (active_alpha) *active_alpha = hb.A.m;
+    if (active_beta) *active_beta = hb.B.m;
+    if (n_tiles) *n_tiles = int32_t(hb.A.panels.size() * hb.B.panels.size());
+    if (max_tile_rows) *max_tile_rows = hb.A.max_panel;
+    if (max_tile_cols) *max_tile_cols = hb.B.max_panel;
+    if (op_indices)
+        for (size_t i = 0; i < hb.ops.size(); ++i) op_indices[i] = hb.ops[i].op_index;
+    return 0;
+}
+
 int tcc_ci_strings_spin(const tcc_plan* p, uint64_t* out_host) {
     if (!p || !out_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
-    for (int64_t i = 0; i < p->hp.nstr; ++i) out_host[i] = p->hp.strings[i];
+    for (int64_t r = 0; r < p->hp.nstr; ++r) out_host[r] = p->hp.strings[p->hp.ref2int[r]];
+    return 0;
+}
+
+int tcc_storage_order(const tcc_plan* p, uint32_t* ref2int_host) {
+    if (!p || !ref2int_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    for (int64_t r = 0; r < p->hp.nstr; ++r) ref2int_host[r] = p->hp.ref2int[r];
     return 0;
 }
 
@@ -335,7 +511,9 @@ int tcc_set_hamiltonian(tcc_plan* p, const double* int1e, const double* int2e) {
             CUDA_TRY(dev_alloc(p, &p->d_hop, size_t(n) * n));
             CUDA_TRY(dev_alloc(p, &p->d_diag2, size_t(n) * n));
             CUDA_TRY(dev_alloc(p, &p->d_binom, bin.size()));
+            CUDA_TRY(dev_alloc(p, &p->d_bitpos, size_t(32)));
         }
+        CUDA_TRY(cudaMemcpy(p->d_bitpos, hp.bitpos.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(p->d_strings, hp.strings.data(), hp.nstr * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(p->d_diag1, d1.data(), n * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(p->d_hop, hop.data(), hop.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -379,7 +557,7 @@ static int apply_h_impl(tcc_plan* p, const double* c, double* sigma, cudaStream_
     HostPlan& hp = p->hp;
     if (!p->has_h) return fail(TCC_ERR_NO_HAMILTONIAN, "tcc_set_hamiltonian has not been called");
     if (hp.hcb) {
-        launch_sigma_hcb(c, sigma, hp.nstr, p->d_strings, hp.n, hp.k, p->d_diag1, p->d_hop, p->d_diag2, p->d_binom, hp.n + 2, st);
+        launch_sigma_hcb(c, sigma, hp.nstr, p->d_strings, hp.n, hp.k, p->d_diag1, p->d_hop, p->d_diag2, p->d_binom, hp.n + 2, p->d_bitpos, st);
         p->launches += 1;
         return 0;
     }
@@ -403,13 +581,21 @@ static int apply_h_impl(tcc_plan* p, const double* c, double* sigma, cudaStream_
     return 0;
 }
 
-int tcc_apply_h(tcc_plan* p, const double* c_dev, double* sigma_dev, void* stream) {
-    if (!p || !c_dev || !sigma_dev) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
-    if (c_dev == sigma_dev) return fail(TCC_ERR_BAD_ARGUMENT, "c and sigma must not alias");
-    if (int rc_dev = use_device(p)) return rc_dev;
-    int rc = apply_h_impl(p, c_dev, sigma_dev, cudaStream_t(stream));
-    if (rc) return rc;
-    CUDA_TRY(cudaGetLastError());
+// ---- sweeps on storage-order vectors ------------------------------------------------------------
+static int prepare_rot(tcc_plan* p, const double* params, cudaStream_t st) {
+    const HostPlan& hp = p->hp;
+    const int m = int(hp.ops.size());
+    if (m == 0) return 0;
+    CUDA_TRY(cudaEventSynchronize(p->rot_event));  // the previous upload has left the pinned buffer
+    for (int j = 0; j < m; ++j) {
+        const double th = params[hp.ops[j].param];
+        const double c = std::cos(th), s = std::sin(th) * hp.ops[j].s0;
+        p->h_rot[j] = make_double2(c, s);
+        p->h_rot[m + j] = make_double2(c, -s);
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_rot_fwd, p->h_rot, sizeof(double2) * m, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->d_rot_rev, p->h_rot + m, sizeof(double2) * m, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(p->rot_event, st));
     return 0;
 }
 
@@ -421,24 +607,117 @@ static void rotate_op(tcc_plan* p, int j, double theta, double* c, cudaStream_t 
     p->launches += 1;
 }
 
-static int civector_impl(tcc_plan* p, const double* params, const double* init_dev, double* out, cudaStream_t st) {
+static void reverse_op(tcc_plan* p, int j, double theta, double* ket, double* bra, double* grad_out, cudaStream_t st) {
+    const OpDesc& op = p->hp.ops[j];
+    p->prof.mark(TCC_PROF_REV_BETA + op.kind, st);
+    launch_reverse(ket, bra, p->hp.nb, row_side(p, op), col_side(p, op), std::cos(theta), -std::sin(theta) * op.s0,
+                   double(op.s0), p->partials, p->ticket, grad_out, st);
+    p->prof.count(TCC_PROF_REV_BETA + op.kind, 1, 64 * p->hp.support_pairs(op));
+    p->launches += 1;
+}
+
+// exp(theta_M G_M) ... exp(theta_1 G_1) applied to a storage-order vector (evolve_civector.py:165-177)
+static int forward_sweep(tcc_plan* p, const double* params, double* vec, cudaStream_t st) {
     HostPlan& hp = p->hp;
-    if (init_dev) {
-        if (init_dev != out) CUDA_TRY(cudaMemcpyAsync(out, init_dev, hp.N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (p->mode == 1) {
+        for (size_t j = 0; j < hp.ops.size(); ++j) rotate_op(p, int(j), params[hp.ops[j].param], vec, st);
     } else {
-        launch_set_unit(out, hp.N, st);
+        if (int rc = prepare_rot(p, params, st)) return rc;
+        p->prof.mark(TCC_PROF_FWD_BATCH, st);
+        const size_t nbt = p->dbatches.size();
+        if (p->btimer.on) p->btimer.ensure(nbt);
+        for (size_t b = 0; b < nbt; ++b) {
+            BatchDevSet& db = p->dbatches[b];
+            if (p->btimer.on) cudaEventRecord(p->btimer.ev[b], st);
+            launch_batch_forward(vec, hp.nb, db.fwd, p->d_rot_fwd, db.smem_fwd, p->batch_threads, st);
+            p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * hp.N);
+            p->launches += 1;
+        }
+        if (p->btimer.on) cudaEventRecord(p->btimer.ev[nbt], st);
+    }
+    p->prof.mark(-1, st);
+    return 0;
+}
+
+// reverse sweep (evolve_civector.py:221-243): grad_ops[j] = <bra| G_j |ket> after undoing factors M..j
+static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double* bra, cudaStream_t st) {
+    HostPlan& hp = p->hp;
+    if (p->mode == 1) {
+        for (int j = int(hp.ops.size()) - 1; j >= 0; --j) reverse_op(p, j, params[hp.ops[j].param], ket, bra, p->grad_ops + j, st);
+    } else {
+        // d_rot_rev was uploaded together with d_rot_fwd by the forward sweep of the same parameters
+        p->prof.mark(TCC_PROF_REV_BATCH, st);
+        const int nbt = int(p->dbatches.size());
+        for (int b = nbt - 1; b >= 0; --b) {
+            BatchDevSet& db = p->dbatches[b];
+            if (p->btimer.on) cudaEventRecord(p->btimer.ev[nbt + 1 + (nbt - 1 - b)], st);
+            launch_batch_reverse(ket, bra, hp.nb, db.rev, p->d_rot_rev, db.smem_rev, p->batch_threads, p->bpart, p->grad_ops, st);
+            p->prof.count(TCC_PROF_REV_BATCH, 2, 32 * hp.N);
+            p->launches += 2;
+        }
+        if (p->btimer.on) cudaEventRecord(p->btimer.ev[2 * nbt + 1], st);
+    }
+    p->prof.mark(-1, st);
+    return 0;
+}
+
+// state preparation into a storage-order buffer
+static int prepare_state(tcc_plan* p, const double* params, const double* init_ref_dev, double* vec, cudaStream_t st) {
+    HostPlan& hp = p->hp;
+    if (init_ref_dev) {
+        to_storage(p, init_ref_dev, vec, st);
+    } else {
+        launch_set_unit(vec, hp.N, p->hf_index, st);
         p->launches += 1;
     }
-    for (size_t j = 0; j < hp.ops.size(); ++j) rotate_op(p, int(j), params[hp.ops[j].param], out, st);
-    p->prof.mark(-1, st);
+    return forward_sweep(p, params, vec, st);
+}
+
+int tcc_apply_h(tcc_plan* p, const double* c_dev, double* sigma_dev, void* stream) {
+    if (!p || !c_dev || !sigma_dev) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    if (c_dev == sigma_dev) return fail(TCC_ERR_BAD_ARGUMENT, "c and sigma must not alias");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    cudaStream_t st = cudaStream_t(stream);
+    if (p->hp.identity_layout) {
+        if (int rc = apply_h_impl(p, c_dev, sigma_dev, st)) return rc;
+    } else {
+        if (int rc = ensure_vec(p, &p->ket)) return rc;
+        if (int rc = ensure_vec(p, &p->bra)) return rc;
+        to_storage(p, c_dev, p->ket, st);
+        if (int rc = apply_h_impl(p, p->ket, p->bra, st)) return rc;
+        from_storage(p, p->bra, sigma_dev, st);
+    }
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 int tcc_civector(tcc_plan* p, const double* params_host, const double* init_dev, double* out_dev, void* stream) {
     if (!p || !out_dev || (!params_host && p->hp.n_params > 0)) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
-    int rc = civector_impl(p, params_host, init_dev, out_dev, cudaStream_t(stream));
-    if (rc) return rc;
+    cudaStream_t st = cudaStream_t(stream);
+    if (p->hp.identity_layout) {
+        if (int rc = prepare_state(p, params_host, init_dev, out_dev, st)) return rc;
+    } else {
+        if (int rc = ensure_vec(p, &p->ket)) return rc;
+        if (int rc = prepare_state(p, params_host, init_dev, p->ket, st)) return rc;
+        from_storage(p, p->ket, out_dev, st);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int tcc_to_storage_order(tcc_plan* p, const double* ref_dev, double* storage_dev, void* stream) {
+    if (!p || !ref_dev || !storage_dev || ref_dev == storage_dev) return fail(TCC_ERR_BAD_ARGUMENT, "null or aliased argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    to_storage(p, ref_dev, storage_dev, cudaStream_t(stream));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int tcc_from_storage_order(tcc_plan* p, const double* storage_dev, double* ref_dev, void* stream) {
+    if (!p || !ref_dev || !storage_dev || ref_dev == storage_dev) return fail(TCC_ERR_BAD_ARGUMENT, "null or aliased argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    from_storage(p, storage_dev, ref_dev, cudaStream_t(stream));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -450,15 +729,6 @@ int tcc_rotate(tcc_plan* p, int j, double theta, double* c_dev, void* stream) {
     rotate_op(p, j, theta, c_dev, cudaStream_t(stream));
     CUDA_TRY(cudaGetLastError());
     return 0;
-}
-
-static void reverse_op(tcc_plan* p, int j, double theta, double* ket, double* bra, double* grad_out, cudaStream_t st) {
-    const OpDesc& op = p->hp.ops[j];
-    p->prof.mark(TCC_PROF_REV_BETA + op.kind, st);
-    launch_reverse(ket, bra, p->hp.nb, row_side(p, op), col_side(p, op), std::cos(theta), -std::sin(theta) * op.s0,
-                   double(op.s0), p->partials, p->ticket, grad_out, st);
-    p->prof.count(TCC_PROF_REV_BETA + op.kind, 1, 64 * p->hp.support_pairs(op));
-    p->launches += 1;
 }
 
 int tcc_reverse_step(tcc_plan* p, int j, double theta, double* ket_dev, double* bra_dev, double* grad_dev, void* stream) {
@@ -475,7 +745,7 @@ static int energy_impl(tcc_plan* p, const double* params, const double* init_dev
     if (!p->has_h) return fail(TCC_ERR_NO_HAMILTONIAN, "tcc_set_hamiltonian has not been called");
     if (int rc = ensure_vec(p, &p->ket)) return rc;
     if (int rc = ensure_vec(p, &p->bra)) return rc;
-    if (int rc = civector_impl(p, params, init_dev, p->ket, st)) return rc;
+    if (int rc = prepare_state(p, params, init_dev, p->ket, st)) return rc;
     if (int rc = apply_h_impl(p, p->ket, p->bra, st)) return rc;
     const int m = int(hp.ops.size());
     p->prof.mark(TCC_PROF_DOT, st);
@@ -483,9 +753,8 @@ static int energy_impl(tcc_plan* p, const double* params, const double* init_dev
     p->prof.count(TCC_PROF_DOT, 1, 16 * hp.N);
     p->prof.mark(-1, st);
     p->launches += 1;
-    if (grad) {
-        for (int j = m - 1; j >= 0; --j) reverse_op(p, j, params[hp.ops[j].param], p->ket, p->bra, p->grad_ops + j, st);
-    }
+    if (grad)
+        if (int rc = reverse_sweep(p, params, p->ket, p->bra, st)) return rc;
     int first = grad ? 0 : m;
     p->prof.mark(-1, st);
     CUDA_TRY(cudaMemcpyAsync(p->pinned + first, p->grad_ops + first, sizeof(double) * (m + 1 - first), cudaMemcpyDeviceToHost, st));
@@ -519,16 +788,27 @@ int tcc_apply_excitation(tcc_plan* p, const double* c_dev, const int32_t* ex_op,
     if (c_dev == out_dev) return fail(TCC_ERR_BAD_ARGUMENT, "input and output must not alias");
     if (int rc_dev = use_device(p)) return rc_dev;
     OpDesc op;
-    int rc = p->hp.make_op(ex_op, ex_op_len, 0, &op);
+    int rc = p->hp.parse_op(ex_op, ex_op_len, 0, &op);
     if (rc) return fail(rc, p->hp.error);
+    p->hp.attach_hops(&op);
     if (op.hop_a >= 0)
         if (int r2 = upload_hop(p, op.hop_a)) return r2;
     if (op.hop_b >= 0)
         if (int r2 = upload_hop(p, op.hop_b)) return r2;
     cudaStream_t st = cudaStream_t(stream);
-    CUDA_TRY(cudaMemsetAsync(out_dev, 0, p->hp.N * sizeof(double), st));
-    launch_apply_g(c_dev, out_dev, p->hp.nb, row_side(p, op), col_side(p, op), double(op.s0), st);
+    const double* src = c_dev;
+    double* dst = out_dev;
+    if (!p->hp.identity_layout) {
+        if (int r2 = ensure_vec(p, &p->ket)) return r2;
+        if (int r2 = ensure_vec(p, &p->bra)) return r2;
+        to_storage(p, c_dev, p->ket, st);
+        src = p->ket;
+        dst = p->bra;
+    }
+    CUDA_TRY(cudaMemsetAsync(dst, 0, p->hp.N * sizeof(double), st));
+    launch_apply_g(src, dst, p->hp.nb, row_side(p, op), col_side(p, op), double(op.s0), st);
     p->launches += 1;
+    if (!p->hp.identity_layout) from_storage(p, p->bra, out_dev, st);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -537,6 +817,28 @@ int tcc_profile_enable(tcc_plan* p, int on) {
     if (!p) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     p->prof.on = on != 0;
     p->prof.reset();
+    return 0;
+}
+
+int tcc_profile_batches(tcc_plan* p, int on, float* fwd_ms, float* rev_ms) {
+    if (!p) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    if (fwd_ms && rev_ms && p->btimer.on) {
+        // timings of the LAST energy_and_grad call (the stream was synchronised by it)
+        const size_t nbt = p->dbatches.size();
+        if (p->btimer.ev.size() >= 2 * nbt + 2) {
+            for (size_t b = 0; b < nbt; ++b) {
+                float t = 0.f;
+                cudaEventElapsedTime(&t, p->btimer.ev[b], p->btimer.ev[b + 1]);
+                fwd_ms[b] = t;
+                t = 0.f;
+                cudaEventElapsedTime(&t, p->btimer.ev[nbt + 1 + (nbt - 1 - b)], p->btimer.ev[nbt + 2 + (nbt - 1 - b)]);
+                rev_ms[b] = t;
+            }
+        }
+        cudaGetLastError();
+    }
+    p->btimer.on = on != 0;
     return 0;
 }
 
@@ -554,25 +856,26 @@ int tcc_profile_read(tcc_plan* p, double* ms, int64_t* launches, int64_t* bytes)
 int tcc_civector_host(tcc_plan* p, const double* params_host, const double* init_host, double* out_host) {
     if (!p || !out_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
-    if (int rc = ensure_vec(p, &p->ket)) return rc;
+    if (int rc = ensure_vec(p, &p->io1)) return rc;
+    if (int rc = ensure_vec(p, &p->io2)) return rc;
     const size_t bytes = p->hp.N * sizeof(double);
-    if (init_host) CUDA_TRY(cudaMemcpy(p->ket, init_host, bytes, cudaMemcpyHostToDevice));
-    int rc = tcc_civector(p, params_host, init_host ? p->ket : nullptr, p->ket, nullptr);
+    if (init_host) CUDA_TRY(cudaMemcpy(p->io1, init_host, bytes, cudaMemcpyHostToDevice));
+    int rc = tcc_civector(p, params_host, init_host ? p->io1 : nullptr, p->io2, nullptr);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpy(out_host, p->ket, bytes, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out_host, p->io2, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 
 int tcc_apply_h_host(tcc_plan* p, const double* c_host, double* sigma_host) {
     if (!p || !c_host || !sigma_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
-    if (int rc = ensure_vec(p, &p->ket)) return rc;
-    if (int rc = ensure_vec(p, &p->bra)) return rc;
+    if (int rc = ensure_vec(p, &p->io1)) return rc;
+    if (int rc = ensure_vec(p, &p->io2)) return rc;
     const size_t bytes = p->hp.N * sizeof(double);
-    CUDA_TRY(cudaMemcpy(p->ket, c_host, bytes, cudaMemcpyHostToDevice));
-    int rc = tcc_apply_h(p, p->ket, p->bra, nullptr);
+    CUDA_TRY(cudaMemcpy(p->io1, c_host, bytes, cudaMemcpyHostToDevice));
+    int rc = tcc_apply_h(p, p->io1, p->io2, nullptr);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpy(sigma_host, p->bra, bytes, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(sigma_host, p->io2, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -582,9 +885,9 @@ int tcc_energy_and_grad_host(tcc_plan* p, const double* params_host, const doubl
     if (int rc_dev = use_device(p)) return rc_dev;
     const double* init_dev = nullptr;
     if (init_host) {
-        if (int rc = ensure_vec(p, &p->ket)) return rc;
-        CUDA_TRY(cudaMemcpy(p->ket, init_host, p->hp.N * sizeof(double), cudaMemcpyHostToDevice));
-        init_dev = p->ket;
+        if (int rc = ensure_vec(p, &p->io1)) return rc;
+        CUDA_TRY(cudaMemcpy(p->io1, init_host, p->hp.N * sizeof(double), cudaMemcpyHostToDevice));
+        init_dev = p->io1;
     }
     if (grad_host) return tcc_energy_and_grad(p, params_host, init_dev, energy_host, grad_host, nullptr);
     return tcc_energy(p, params_host, init_dev, energy_host, nullptr);
@@ -593,13 +896,13 @@ int tcc_energy_and_grad_host(tcc_plan* p, const double* params_host, const doubl
 int tcc_apply_excitation_host(tcc_plan* p, const double* c_host, const int32_t* ex_op, int ex_op_len, double* out_host) {
     if (!p || !c_host || !out_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
-    if (int rc = ensure_vec(p, &p->ket)) return rc;
-    if (int rc = ensure_vec(p, &p->bra)) return rc;
+    if (int rc = ensure_vec(p, &p->io1)) return rc;
+    if (int rc = ensure_vec(p, &p->io2)) return rc;
     const size_t bytes = p->hp.N * sizeof(double);
-    CUDA_TRY(cudaMemcpy(p->ket, c_host, bytes, cudaMemcpyHostToDevice));
-    int rc = tcc_apply_excitation(p, p->ket, ex_op, ex_op_len, p->bra, nullptr);
+    CUDA_TRY(cudaMemcpy(p->io1, c_host, bytes, cudaMemcpyHostToDevice));
+    int rc = tcc_apply_excitation(p, p->io1, ex_op, ex_op_len, p->io2, nullptr);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpy(out_host, p->bra, bytes, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out_host, p->io2, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 

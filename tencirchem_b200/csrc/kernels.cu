@@ -241,16 +241,16 @@ void launch_apply_g(const double* c, double* out, int64_t nb, SideList rows, Sid
 // ------------------------------------------------------------------------------------------------
 // vector utilities
 // ------------------------------------------------------------------------------------------------
-__global__ void set_unit_kernel(double* c, int64_t n) {
+__global__ void set_unit_kernel(double* c, int64_t n, int64_t one_at) {
     int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    for (; i < n; i += stride) c[i] = (i == 0) ? 1.0 : 0.0;
+    for (; i < n; i += stride) c[i] = (i == one_at) ? 1.0 : 0.0;
 }
 
-void launch_set_unit(double* c, int64_t n, cudaStream_t st) {
+void launch_set_unit(double* c, int64_t n, int64_t one_at, cudaStream_t st) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    set_unit_kernel<<<unsigned(blocks), 256, 0, st>>>(c, n);
+    set_unit_kernel<<<unsigned(blocks), 256, 0, st>>>(c, n, one_at);
 }
 
 __global__ void __launch_bounds__(256) dot_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
@@ -457,7 +457,7 @@ void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, con
 __global__ void sigma_hcb_kernel(const double* __restrict__ c, double* __restrict__ sigma, int64_t nstr,
                                  const uint32_t* __restrict__ strings, int n, const double* __restrict__ diag1,
                                  const double* __restrict__ hop, const double* __restrict__ diag2,
-                                 const int64_t* __restrict__ binom, int binom_ld) {
+                                 const int64_t* __restrict__ binom, int binom_ld, const int* __restrict__ bitpos) {
     int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nstr) return;
     uint32_t s = strings[i];
@@ -469,9 +469,12 @@ __global__ void sigma_hcb_kernel(const double* __restrict__ c, double* __restric
             bool oq = (s >> q) & 1u;
             if (op != oq) {
                 uint32_t t = s ^ (1u << p) ^ (1u << q);
+                // storage address = rank of the string with its bits moved to their storage positions
+                uint32_t tp = 0;
+                for (uint32_t x = t; x; x &= x - 1) tp |= 1u << bitpos[__ffs(x) - 1];
                 int64_t r = 0;
                 int idx = 1;
-                for (uint32_t x = t; x; x &= x - 1) {
+                for (uint32_t x = tp; x; x &= x - 1) {
                     r += binom[(__ffs(x) - 1) * binom_ld + idx];
                     ++idx;
                 }
@@ -486,10 +489,10 @@ __global__ void sigma_hcb_kernel(const double* __restrict__ c, double* __restric
 
 void launch_sigma_hcb(const double* c, double* sigma, int64_t nstr, const uint32_t* strings, int n, int k,
                       const double* diag1, const double* hop, const double* diag2, const int64_t* binom, int binom_ld,
-                      cudaStream_t st) {
+                      const int* bitpos, cudaStream_t st) {
     (void)k;
     unsigned blocks = unsigned((nstr + 127) / 128);
-    sigma_hcb_kernel<<<blocks, 128, 0, st>>>(c, sigma, nstr, strings, n, diag1, hop, diag2, binom, binom_ld);
+    sigma_hcb_kernel<<<blocks, 128, 0, st>>>(c, sigma, nstr, strings, n, diag1, hop, diag2, binom, binom_ld, bitpos);
 }
 
 }  // namespace tcc

@@ -28,7 +28,7 @@ void launch_apply_g(const double* c, double* out, int64_t nb, SideList rows, Sid
                     cudaStream_t st);
 int reverse_partials_capacity();
 
-void launch_set_unit(double* c, int64_t n, cudaStream_t st);
+void launch_set_unit(double* c, int64_t n, int64_t one_at, cudaStream_t st);
 // deterministic dot product: out[0] = sum x*y
 void launch_dot(const double* x, const double* y, int64_t n, double* partials, unsigned* ticket,
                 double* out, cudaStream_t st);
@@ -43,6 +43,6 @@ void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, con
 // hard-core-boson sigma (hamiltonian.py:158-183)
 void launch_sigma_hcb(const double* c, double* sigma, int64_t nstr, const uint32_t* strings, int n, int k,
                       const double* diag1, const double* hop, const double* diag2, const int64_t* binom,
-                      int binom_ld, cudaStream_t st);
+                      int binom_ld, const int* bitpos, cudaStream_t st);
 
 }  // namespace tcc

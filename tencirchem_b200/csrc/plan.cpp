@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <numeric>
 #include <thread>
 #include <unordered_map>
 
@@ -49,39 +50,36 @@ int HostPlan::init(int n_qubits_, int n_elec_, int hcb_) {
         error = "Too many qubits: more than 2^31 strings per spin";
         return TCC_ERR_TOO_MANY_QUBITS;
     }
-    strings.resize(nstr);
-    if (k == 0) {
-        strings[0] = 0;
-    } else {
-        uint64_t v = (uint64_t(1) << k) - 1;
-        for (int64_t i = 0; i < nstr; ++i) {
-            strings[i] = uint32_t(v);
-            uint64_t t = v | (v - 1);  // Gosper: next integer with the same popcount
-            v = (t + 1) | (((~t & (t + 1)) - 1) >> (__builtin_ctzll(v) + 1));
-        }
-    }
     na = hcb ? 1 : nstr;
     nb = nstr;
     N = na * nb;
+    bitpos.resize(n);
+    std::iota(bitpos.begin(), bitpos.end(), 0);
     return 0;
 }
 
-int64_t HostPlan::rank(uint32_t s) const {
+uint32_t HostPlan::permute_bits(uint32_t s) const {
+    if (identity_layout) return s;
+    uint32_t t = 0;
+    for (uint32_t x = s; x; x &= x - 1) t |= 1u << bitpos[__builtin_ctz(x)];
+    return t;
+}
+
+int64_t HostPlan::colex_rank(uint32_t t) const {
     int64_t r = 0;
     int i = 1;
-    while (s) {
-        int p = __builtin_ctz(s);
-        r += binom[p][i];
+    while (t) {
+        r += binom[__builtin_ctz(t)][i];
         ++i;
-        s &= s - 1;
+        t &= t - 1;
     }
     return r;
 }
 
-int64_t HostPlan::rank_or_zero(uint64_t s) const {
+int64_t HostPlan::ref_rank_or_zero(uint64_t s) const {
     if (s >> n) return 0;
     if (popc(s) != k) return 0;
-    return rank(uint32_t(s));
+    return colex_rank(uint32_t(s));
 }
 
 static uint32_t zmask_of(uint32_t bits) {
@@ -116,7 +114,7 @@ int HostPlan::find_or_build_hop(uint32_t cre, uint32_t ann) {
     return id;
 }
 
-int HostPlan::make_op(const int32_t* idx, int len, int param, OpDesc* op) {
+int HostPlan::parse_op(const int32_t* idx, int len, int param, OpDesc* op) {
     auto fmt = [&]() {
         std::string s = "(";
         for (int i = 0; i < len; ++i) s += std::to_string(idx[i]) + (i + 1 < len ? ", " : "");
@@ -138,6 +136,7 @@ int HostPlan::make_op(const int32_t* idx, int len, int param, OpDesc* op) {
         }
         seen |= uint64_t(1) << idx[i];
     }
+    *op = OpDesc();
     op->len = len;
     op->param = param;
     for (int i = 0; i < 4; ++i) op->idx[i] = i < len ? idx[i] : 0;
@@ -145,9 +144,11 @@ int HostPlan::make_op(const int32_t* idx, int len, int param, OpDesc* op) {
     for (int i = 0; i < len / 2; ++i) cre |= uint64_t(1) << idx[i];
     for (int i = len / 2; i < len; ++i) ann |= uint64_t(1) << idx[i];
     uint64_t lo = (uint64_t(1) << n) - 1;
-    uint32_t cre_b = uint32_t(cre & lo), ann_b = uint32_t(ann & lo);
-    uint32_t cre_a = hcb ? 0u : uint32_t(cre >> n), ann_a = hcb ? 0u : uint32_t(ann >> n);
-    if (popc(cre_a) != popc(ann_a) || popc(cre_b) != popc(ann_b)) {
+    op->cre_b = uint32_t(cre & lo);
+    op->ann_b = uint32_t(ann & lo);
+    op->cre_a = hcb ? 0u : uint32_t(cre >> n);
+    op->ann_a = hcb ? 0u : uint32_t(ann >> n);
+    if (popc(op->cre_a) != popc(op->ann_a) || popc(op->cre_b) != popc(op->ann_b)) {
         // the reference silently mis-computes these: partner falls outside the CI space
         error = "Excitation " + fmt() + " not supported: it does not conserve the electron number per spin";
         return TCC_ERR_BAD_EXCITATION;
@@ -160,14 +161,14 @@ int HostPlan::make_op(const int32_t* idx, int len, int param, OpDesc* op) {
         int s_t = ((idx[2] < idx[3]) ^ (idx[1] < idx[0])) ? -1 : 1;
         op->s0 = -s_t;
     }
-    op->hop_a = (cre_a | ann_a) ? find_or_build_hop(cre_a, ann_a) : -1;
-    op->hop_b = (cre_b | ann_b) ? find_or_build_hop(cre_b, ann_b) : -1;
-    op->kind = op->hop_a < 0 ? OP_BETA : (op->hop_b < 0 ? OP_ALPHA : OP_ALPHABETA);
-    if (hcb && op->hop_a >= 0) {
-        error = "internal: alpha hop in an hcb plan";
-        return TCC_ERR_BAD_EXCITATION;
-    }
+    bool has_a = (op->cre_a | op->ann_a) != 0, has_b = (op->cre_b | op->ann_b) != 0;
+    op->kind = !has_a ? OP_BETA : (!has_b ? OP_ALPHA : OP_ALPHABETA);
     return 0;
+}
+
+void HostPlan::attach_hops(OpDesc* op) {
+    op->hop_a = (op->cre_a | op->ann_a) ? find_or_build_hop(op->cre_a, op->ann_a) : -1;
+    op->hop_b = (op->cre_b | op->ann_b) ? find_or_build_hop(op->cre_b, op->ann_b) : -1;
 }
 
 int64_t HostPlan::support_pairs(const OpDesc& op) const {
@@ -177,32 +178,33 @@ int64_t HostPlan::support_pairs(const OpDesc& op) const {
 }
 
 void HostPlan::expand_tables(const OpDesc& op, uint64_t* perm, int8_t* phase, int8_t* f2) const {
-    // partner address for EVERY determinant, including the reference's "invalid string -> 0" rule
+    // partner address for EVERY determinant, including the reference's "invalid string -> 0" rule;
+    // everything here is in REFERENCE order
     uint64_t mask = 0;
     for (int i = 0; i < op.len; ++i) mask |= uint64_t(1) << op.idx[i];
     uint64_t lo = (uint64_t(1) << n) - 1;
     uint32_t mb = uint32_t(mask & lo), ma = hcb ? 0u : uint32_t(mask >> n);
     std::vector<int64_t> pa(na), pb(nb);
-    for (int64_t a = 0; a < na; ++a) pa[a] = hcb ? 0 : rank_or_zero(uint64_t(strings[a]) ^ ma);
-    for (int64_t b = 0; b < nb; ++b) pb[b] = rank_or_zero(uint64_t(strings[b]) ^ mb);
+    for (int64_t a = 0; a < na; ++a) pa[a] = hcb ? 0 : ref_rank_or_zero(uint64_t(strings[ref2int[a]]) ^ ma);
+    for (int64_t b = 0; b < nb; ++b) pb[b] = ref_rank_or_zero(uint64_t(strings[ref2int[b]]) ^ mb);
     for (int64_t a = 0; a < na; ++a)
         for (int64_t b = 0; b < nb; ++b) {
             perm[a * nb + b] = uint64_t(pa[a] * nstr + pb[b]);
             phase[a * nb + b] = 0;
             f2[a * nb + b] = 0;
         }
-    static const std::vector<uint32_t> empty;
     const HopTable* ha = op.hop_a >= 0 ? &hops[op.hop_a] : nullptr;
     const HopTable* hb = op.hop_b >= 0 ? &hops[op.hop_b] : nullptr;
     int64_t la = ha ? int64_t(ha->src.size()) : na;
     int64_t lb = hb ? int64_t(hb->src.size()) : nb;
+    auto to_ref = [&](int64_t x) { return hcb && na == 1 && false ? x : int64_t(int2ref[x]); };
     for (int64_t i = 0; i < la; ++i) {
-        int64_t a = ha ? ha->src[i] : i;
-        int64_t a2 = ha ? (ha->dst[i] & 0x7fffffffu) : i;
+        int64_t a = ha ? to_ref(ha->src[i]) : i;
+        int64_t a2 = ha ? to_ref(ha->dst[i] & 0x7fffffffu) : i;
         int sa = ha ? int(ha->dst[i] >> 31) : 0;
         for (int64_t j = 0; j < lb; ++j) {
-            int64_t b = hb ? hb->src[j] : j;
-            int64_t b2 = hb ? (hb->dst[j] & 0x7fffffffu) : j;
+            int64_t b = hb ? to_ref(hb->src[j]) : j;
+            int64_t b2 = hb ? to_ref(hb->dst[j] & 0x7fffffffu) : j;
             int sb = hb ? int(hb->dst[j] >> 31) : 0;
             int p = (sa ^ sb) ? -op.s0 : op.s0;
             int64_t I = a * nb + b, J = a2 * nb + b2;
@@ -212,6 +214,351 @@ void HostPlan::expand_tables(const OpDesc& op, uint64_t* perm, int8_t* phase, in
             f2[J] = -1;
         }
     }
+}
+
+// ---- batch schedule ----------------------------------------------------------------------------
+int64_t HostPlan::max_class(int m) const {
+    int lo = std::max(0, k - (n - m)), hi = std::min(m, k);
+    int64_t best = 1;
+    for (int e = lo; e <= hi; ++e) best = std::max(best, binom[m][e]);
+    return best;
+}
+
+std::vector<std::vector<int>> HostPlan::group_ops(int tile_elems) const {
+    // Greedy list scheduling.  An excitation joins the open batch if the enlarged active sets still give
+    // tiles that fit on chip AND it commutes with every excitation that was skipped before it (disjoint
+    // spin-orbital sets => the generators commute), so the product of factors is unchanged.
+    std::vector<std::vector<int>> groups;
+    std::vector<int> remaining(ops.size());
+    std::iota(remaining.begin(), remaining.end(), 0);
+    const size_t window = 8192;
+    const size_t max_ops = 256;
+    const uint32_t all = n >= 32 ? 0xffffffffu : ((1u << n) - 1);
+    while (!remaining.empty()) {
+        std::vector<int> batch, rest;
+        uint32_t sa = 0, sb = 0, skip_a = 0, skip_b = 0;
+        bool closed = false;
+        for (size_t i = 0; i < remaining.size(); ++i) {
+            int j = remaining[i];
+            if (closed || i >= window || batch.size() >= max_ops) {
+                rest.push_back(j);
+                continue;
+            }
+            const OpDesc& op = ops[j];
+            uint32_t oa = op.cre_a | op.ann_a, ob = op.cre_b | op.ann_b;
+            bool blocked = (oa & skip_a) || (ob & skip_b);
+            if (!blocked) {
+                uint32_t nsa = sa | oa, nsb = sb | ob;
+                int64_t elems = max_class(hcb ? 0 : popc(nsa)) * max_class(popc(nsb));
+                if (elems <= tile_elems || batch.empty()) {
+                    batch.push_back(j);
+                    sa = nsa;
+                    sb = nsb;
+                    continue;
+                }
+            }
+            rest.push_back(j);
+            skip_a |= oa;
+            skip_b |= ob;
+            if ((hcb || skip_a == all) && skip_b == all) closed = true;
+        }
+        groups.push_back(std::move(batch));
+        remaining.swap(rest);
+    }
+    return groups;
+}
+
+void HostPlan::choose_layout(const std::vector<std::vector<int>>& groups, bool use_layout) {
+    std::iota(bitpos.begin(), bitpos.end(), 0);
+    identity_layout = true;
+    if (!use_layout || groups.empty()) return;
+    // orbitals that are active in many (large) batches go to the low bit positions: the strings of a
+    // class then differ in the fastest-varying positions and sit next to each other in memory
+    std::vector<double> weight(n, 0.0);
+    for (const auto& g : groups) {
+        uint32_t s = 0;
+        for (int j : g) s |= ops[j].cre_a | ops[j].ann_a | ops[j].cre_b | ops[j].ann_b;
+        for (int o = 0; o < n; ++o)
+            if (s >> o & 1) weight[o] += double(g.size());
+    }
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight[x] > weight[y]; });
+    for (int pos = 0; pos < n; ++pos) bitpos[order[pos]] = pos;
+    for (int o = 0; o < n; ++o)
+        if (bitpos[o] != o) identity_layout = false;
+}
+
+void HostPlan::build_strings() {
+    strings.resize(nstr);
+    ref2int.resize(nstr);
+    int2ref.resize(nstr);
+    std::vector<int> invpos(n);
+    for (int o = 0; o < n; ++o) invpos[bitpos[o]] = o;
+    uint64_t v = k ? (uint64_t(1) << k) - 1 : 0;
+    for (int64_t i = 0; i < nstr; ++i) {
+        uint32_t s = 0;
+        for (uint64_t x = v; x; x &= x - 1) s |= 1u << invpos[__builtin_ctzll(x)];
+        strings[i] = s;
+        int64_t r = colex_rank(s);
+        ref2int[r] = uint32_t(i);
+        int2ref[i] = uint32_t(r);
+        if (k) {
+            uint64_t t = v | (v - 1);  // Gosper: next integer with the same popcount
+            v = (t + 1) | (((~t & (t + 1)) - 1) >> (__builtin_ctzll(v) + 1));
+        }
+    }
+}
+
+void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string) {
+    side->S = S;
+    side->m = popc(S);
+    const int m = side->m;
+    const int64_t count = single_string ? 1 : nstr;
+    // classes in order of first appearance (= ascending first address), members in address order
+    std::unordered_map<uint32_t, int> cls_of;
+    std::vector<std::vector<uint32_t>> members;
+    std::vector<uint32_t> cls_sigma;
+    std::vector<int> cls_e;
+    for (int64_t a = 0; a < count; ++a) {
+        uint32_t s = single_string ? 0u : strings[a];
+        uint32_t sig = s & ~S;
+        auto it = cls_of.find(sig);
+        int id;
+        if (it == cls_of.end()) {
+            id = int(members.size());
+            cls_of.emplace(sig, id);
+            members.emplace_back();
+            cls_sigma.push_back(sig);
+            cls_e.push_back(popc(s & S));
+        } else {
+            id = it->second;
+        }
+        members[id].push_back(uint32_t(a));
+    }
+    side->addr.clear();
+    side->ord.clear();
+    side->addr_sorted.clear();
+    side->sigma.clear();
+    side->panels.clear();
+    side->max_panel = 0;
+    side->max_classes = 0;
+    for (int e = 0; e <= m; ++e) {
+        std::vector<int> ids;
+        for (size_t c = 0; c < members.size(); ++c)
+            if (cls_e[c] == e) ids.push_back(int(c));
+        if (ids.empty()) continue;
+        const int csize = int(members[ids[0]].size());
+        // an active side keeps one class per panel (the kernels rely on it); a side without active orbitals
+        // packs single-string classes up to the panel target
+        const int per_panel = m > 0 ? 1 : std::max(1, std::min(panel_target, 4096));
+        for (size_t p0 = 0; p0 < ids.size(); p0 += per_panel) {
+            size_t p1 = std::min(ids.size(), p0 + per_panel);
+            PanelDesc pd;
+            pd.off = uint32_t(side->addr.size());
+            pd.class_off = uint32_t(side->sigma.size());
+            pd.G = uint16_t(p1 - p0);
+            pd.c = uint16_t(csize);
+            pd.e = uint16_t(e);
+            pd.pad = 0;
+            for (size_t q = p0; q < p1; ++q) {
+                side->sigma.push_back(cls_sigma[ids[q]]);
+                for (uint32_t a : members[ids[q]]) side->addr.push_back(a);
+            }
+            const int rows = int(pd.G) * csize;
+            std::vector<uint16_t> ord(rows);
+            std::iota(ord.begin(), ord.end(), uint16_t(0));
+            const uint32_t* base = side->addr.data() + pd.off;
+            std::sort(ord.begin(), ord.end(), [&](uint16_t x, uint16_t y) { return base[x] < base[y]; });
+            side->ord.insert(side->ord.end(), ord.begin(), ord.end());
+            for (uint16_t x : ord) side->addr_sorted.push_back(base[x]);
+            side->panels.push_back(pd);
+            side->max_panel = std::max(side->max_panel, rows);
+            side->max_classes = std::max(side->max_classes, int(pd.G));
+        }
+    }
+}
+
+static uint32_t compress_bits(uint32_t bits, const std::vector<int>& act) {
+    uint32_t t = 0;
+    for (size_t i = 0; i < act.size(); ++i)
+        if (bits >> act[i] & 1) t |= 1u << i;
+    return t;
+}
+
+void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch* out) {
+    uint32_t sa = 0, sb = 0;
+    for (int j : group) {
+        sa |= ops[j].cre_a | ops[j].ann_a;
+        sb |= ops[j].cre_b | ops[j].ann_b;
+    }
+    // Pad the active sets with unused orbitals (lowest storage positions first) while the tiles still fit:
+    // small active sets would split the space into a huge number of tiny classes.
+    {
+        std::vector<int> by_pos(n);
+        std::iota(by_pos.begin(), by_pos.end(), 0);
+        std::sort(by_pos.begin(), by_pos.end(), [&](int x, int y) { return bitpos[x] < bitpos[y]; });
+        bool grew = true;
+        while (grew) {
+            grew = false;
+            // grow the smaller side first so that tiles stay roughly square
+            for (int pass = 0; pass < 2 && !grew; ++pass) {
+                bool beta = (popc(sb) <= popc(sa)) ? pass == 0 : pass == 1;
+                if (!beta && (hcb || sa == 0)) continue;  // a side without hops stays unexpanded
+                if (beta && sb == 0) continue;
+                uint32_t& s = beta ? sb : sa;
+                for (int o : by_pos) {
+                    if (s >> o & 1) continue;
+                    uint32_t ns = s | (1u << o);
+                    int64_t elems = beta ? max_class(hcb ? 0 : popc(sa)) * max_class(popc(ns))
+                                         : max_class(popc(ns)) * max_class(popc(sb));
+                    if (elems <= tile_elems) {
+                        s = ns;
+                        grew = true;
+                    }
+                    break;
+                }
+            }
+        }
+    }
+    int64_t ca = max_class(hcb ? 0 : popc(sa)), cb = max_class(popc(sb));
+    int64_t pa = ca, pb = cb;
+    // spend the remaining capacity: first make the contiguous (beta) direction at least 128 wide, then rows
+    while (pa * pb * 2 <= tile_elems) {
+        if (pb < 128 && pb * 2 <= nb)
+            pb *= 2;
+        else if (pa * 2 <= na)
+            pa *= 2;
+        else if (pb * 2 <= nb)
+            pb *= 2;
+        else
+            break;
+    }
+    build_side(sa, int(pa), &out->A, hcb != 0);
+    build_side(sb, int(pb), &out->B, false);
+    auto make_tables = [&](SideBatch& side) {
+        const int m = side.m;
+        std::vector<int> act;  // active orbitals sorted by storage bit position
+        for (int o = 0; o < n; ++o)
+            if (side.S >> o & 1) act.push_back(o);
+        std::sort(act.begin(), act.end(), [&](int x, int y) { return bitpos[x] < bitpos[y]; });
+        side.tab.clear();
+        side.tab_index.assign(side.hops.size() * size_t(m + 1) * 2, 0);
+        for (size_t h = 0; h < side.hops.size(); ++h) {
+            const LocalHop& lh = side.hops[h];
+            for (int e = 0; e <= m; ++e) {
+                int32_t off = int32_t(side.tab.size()), cnt = 0;
+                if (e >= popc(lh.ann) && e <= m) {
+                    // all patterns of e bits among m compressed positions, ascending = class-local order
+                    uint32_t v = e ? (1u << e) - 1 : 0;
+                    int64_t total = binom[m][e];
+                    for (int64_t r = 0; r < total; ++r) {
+                        uint32_t bits = 0;
+                        for (uint32_t x = v; x; x &= x - 1) bits |= 1u << act[__builtin_ctz(x)];
+                        if ((bits & lh.ann) == lh.ann && (bits & lh.cre) == 0) {
+                            uint32_t nb_ = bits ^ (lh.cre | lh.ann);
+                            uint32_t dst = uint32_t(colex_rank(compress_bits(nb_, act)));
+                            uint32_t sg = popc(bits & lh.zmask) & 1;
+                            side.tab.push_back(uint32_t(r) | (dst << 15) | (sg << 30));
+                            ++cnt;
+                        }
+                        if (e) {
+                            uint32_t t = v | (v - 1);
+                            v = (t + 1) | (((~t & (t + 1)) - 1) >> (__builtin_ctz(v) + 1));
+                        }
+                    }
+                }
+                side.tab_index[(h * (m + 1) + e) * 2 + 0] = off;
+                side.tab_index[(h * (m + 1) + e) * 2 + 1] = cnt;
+            }
+        }
+        if (side.tab.empty()) side.tab.push_back(0);
+        if (side.tab_index.empty()) side.tab_index.assign(2, 0);
+    };
+    auto local_hop = [&](SideBatch& side, uint32_t cre, uint32_t ann) -> int {
+        if (!(cre | ann)) return -1;
+        for (size_t h = 0; h < side.hops.size(); ++h)
+            if (side.hops[h].cre == cre && side.hops[h].ann == ann) return int(h);
+        side.hops.push_back(LocalHop{cre, ann, hcb ? 0u : zmask_of(cre | ann)});
+        return int(side.hops.size()) - 1;
+    };
+    out->A.hops.clear();
+    out->B.hops.clear();
+    out->ops.clear();
+    for (int j : group) {
+        const OpDesc& op = ops[j];
+        BatchOp bo;
+        bo.op_index = j;
+        bo.h_a = local_hop(out->A, op.cre_a, op.ann_a);
+        bo.h_b = local_hop(out->B, op.cre_b, op.ann_b);
+        bo.zspec_a = bo.h_a >= 0 ? (out->A.hops[bo.h_a].zmask & ~sa) : 0u;
+        bo.zspec_b = bo.h_b >= 0 ? (out->B.hops[bo.h_b].zmask & ~sb) : 0u;
+        bo.s0 = op.s0;
+        out->ops.push_back(bo);
+    }
+    make_tables(out->A);
+    make_tables(out->B);
+
+    // fully expanded pair lists per (excitation, e_alpha, e_beta)
+    const int ma = out->A.m, mb = out->B.m;
+    out->ld_fixed = out->B.max_panel | 1;
+    out->plist.clear();
+    out->plist_index.assign(out->ops.size() * size_t(ma + 1) * (mb + 1) * 2, 0);
+    std::vector<char> has_ea(ma + 1, 0), has_eb(mb + 1, 0);
+    for (const auto& pd : out->A.panels) has_ea[pd.e] = 1;
+    for (const auto& pd : out->B.panels) has_eb[pd.e] = 1;
+    struct Ent {
+        uint32_t s, d, sg;
+    };
+    auto side_entries = [&](const SideBatch& side, int h, int e, std::vector<Ent>* v) {
+        v->clear();
+        if (side.m == 0) {  // repeated by the kernel
+            v->push_back(Ent{0, 0, 0});
+            return;
+        }
+        if (h < 0) {
+            int64_t c = binom[side.m][e];
+            for (int64_t i = 0; i < c; ++i) v->push_back(Ent{uint32_t(i), uint32_t(i), 0});
+            return;
+        }
+        const int32_t off = side.tab_index[(size_t(h) * (side.m + 1) + e) * 2];
+        const int32_t cnt = side.tab_index[(size_t(h) * (side.m + 1) + e) * 2 + 1];
+        for (int32_t i = 0; i < cnt; ++i) {
+            uint32_t t = side.tab[off + i];
+            v->push_back(Ent{t & 0x7fffu, (t >> 15) & 0x7fffu, t >> 30});
+        }
+    };
+    std::vector<Ent> ea_list, eb_list;
+    for (size_t t = 0; t < out->ops.size(); ++t) {
+        const BatchOp& bo = out->ops[t];
+        for (int ea = 0; ea <= ma; ++ea) {
+            if (!has_ea[ea]) continue;
+            side_entries(out->A, bo.h_a, ea, &ea_list);
+            for (int eb = 0; eb <= mb; ++eb) {
+                if (!has_eb[eb]) continue;
+                side_entries(out->B, bo.h_b, eb, &eb_list);
+                const uint32_t ld = mb > 0 ? (uint32_t(binom[mb][eb]) | 1u) : uint32_t(out->ld_fixed);
+                const size_t slot = ((t * (ma + 1) + ea) * (mb + 1) + eb) * 2;
+                out->plist_index[slot] = int32_t(out->plist.size());
+                out->plist_index[slot + 1] = int32_t(ea_list.size() * eb_list.size());
+                for (const Ent& a : ea_list)
+                    for (const Ent& b : eb_list)
+                        out->plist.push_back((a.s * ld + b.s) | ((a.d * ld + b.d) << 15) | ((a.sg ^ b.sg) << 30));
+            }
+        }
+    }
+    if (out->plist.empty()) out->plist.push_back(0);
+}
+
+void HostPlan::finalize(int tile_elems, bool use_layout) {
+    tile_elems = std::max(tile_elems, 64);
+    std::vector<std::vector<int>> groups = group_ops(tile_elems);
+    choose_layout(groups, use_layout);
+    build_strings();
+    for (auto& op : ops) attach_hops(&op);
+    batches.clear();
+    batches.resize(groups.size());
+    for (size_t g = 0; g < groups.size(); ++g) build_batch(groups[g], tile_elems, &batches[g]);
 }
 
 void HostPlan::build_links() {

@@ -1,12 +1,20 @@
-// Host-side plan of the B200 civector engine: CI strings, per-spin hop tables, op descriptors,
-// single-replacement link tables and the string-space Hamiltonian.  Plain C++ (no CUDA types)
-// so the same code is used by the device engine and by the host-only introspection calls.
+// Host-side plan of the B200 civector engine: CI strings, per-spin hop tables, op descriptors, the
+// batch schedule with its closed tiles, single-replacement link tables and the string-space
+// Hamiltonian.  Plain C++ (no CUDA types) so the same code serves the device engine and the host-only
+// introspection calls.
 //
 // What it replaces in the reference (paths relative to /root/reference):
 //   tencirchem/static/ci_utils.py:16-49            CI strings and addresses
 //   tencirchem/static/evolve_civector.py:24-106    partner index / support class / fermionic sign
 // The reference stores [M, N] tables; everything factorises per spin string, so the
 // plan keeps one compact list of (source address, partner address, sign) per DISTINCT spin hop.
+//
+// STORAGE ORDER.  Inside the engine the CI matrix is stored with the spin strings in a plan-specific
+// order: the orbitals are renumbered by a bit permutation `bitpos` (most frequently active orbitals
+// in the lowest positions) and strings are sorted as integers of the permuted bits.  That makes the
+// closed tiles of a batch (below) nearly contiguous in memory.  `rank()` is the storage address,
+// `ref_rank()` the reference address (ascending integers of the ORIGINAL bits, ci_utils.py:22);
+// vectors crossing the C ABI are always in reference order.
 #pragma once
 #include <cstdint>
 #include <map>
@@ -16,15 +24,16 @@
 namespace tcc {
 
 struct HopTable {
-    uint32_t cre = 0, ann = 0, zmask = 0;  // spin-local bit masks
-    std::vector<uint32_t> src;             // strings with ann occupied & cre empty ("positive"), ascending address
-    std::vector<uint32_t> dst;             // partner address | (parity(src_string & zmask) << 31)
+    uint32_t cre = 0, ann = 0, zmask = 0;  // spin-local bit masks (original orbital numbering)
+    std::vector<uint32_t> src;             // storage addresses of strings with ann occupied & cre empty, ascending
+    std::vector<uint32_t> dst;             // partner storage address | (parity(src_string & zmask) << 31)
 };
 
 enum OpKind : int { OP_BETA = 0, OP_ALPHA = 1, OP_ALPHABETA = 2 };
 
 struct OpDesc {
     int kind = 0;
+    uint32_t cre_a = 0, ann_a = 0, cre_b = 0, ann_b = 0;
     int hop_a = -1, hop_b = -1;  // indices into HostPlan::hops (-1 = identity on that spin)
     int s0 = 1;                  // global sign of the JW string
     int param = 0;
@@ -39,41 +48,111 @@ struct Link {       // E_pq |string> = sgn |addr>
     int8_t pad;
 };
 
+// ---- batch schedule --------------------------------------------------------------------------
+// A batch is a run of excitations (in application order, after provably commuting swaps) whose
+// orbitals lie inside the active sets (S_alpha, S_beta).  Strings split into classes by the
+// occupation of the spectator orbitals; a class is closed under every hop of the batch, so a tile
+// = (panel of alpha classes) x (panel of beta classes) can be rotated on-chip by the whole batch.
+struct PanelDesc {
+    uint32_t off;        // first entry of the panel in SideBatch::addr / ::ord
+    uint32_t class_off;  // first class of the panel in SideBatch::sigma
+    uint16_t G;          // classes in the panel
+    uint16_t c;          // strings per class
+    uint16_t e;          // active electrons per class
+    uint16_t pad;
+};
+
+struct LocalHop {
+    uint32_t cre, ann, zmask;
+};
+
+struct SideBatch {
+    uint32_t S = 0;  // active orbitals (original numbering)
+    int m = 0;
+    std::vector<uint32_t> addr;    // [nstr] storage addresses, panel-major, class-major, local order
+    std::vector<uint16_t> ord;     // [nstr] per panel: local indices sorted by storage address
+    std::vector<uint32_t> addr_sorted;  // [nstr] per panel: addr[ord[t]] (ascending inside a panel)
+    std::vector<uint32_t> sigma;   // per class: spectator bits
+    std::vector<PanelDesc> panels;
+    std::vector<LocalHop> hops;
+    std::vector<uint32_t> tab;         // entries src | dst << 15 | sign << 30 (class-local indices)
+    std::vector<int32_t> tab_index;    // [n_hops][m + 1][2] = (offset, count)
+    int max_panel = 0;                 // largest panel (strings)
+    int max_classes = 0;               // largest number of classes in a panel
+};
+
+struct BatchOp {
+    int32_t op_index;
+    int32_t h_a, h_b;  // local hop ids (-1 = identity)
+    uint32_t zspec_a, zspec_b;
+    int32_t s0;
+};
+
+struct Batch {
+    SideBatch A, B;
+    std::vector<BatchOp> ops;  // application order of the forward sweep
+    // Fully expanded pair lists: for excitation t and a tile whose classes hold (e_a, e_b) active electrons,
+    // entries i1 | i2 << 15 | sign << 30 with i = local_row * ld + local_col (ld = tile columns | 1).
+    // A side without active orbitals is not expanded: the kernel repeats the list over its rows / columns.
+    std::vector<uint32_t> plist;
+    std::vector<int32_t> plist_index;  // [n_ops][m_a + 1][m_b + 1][2] = (offset, count)
+    int ld_fixed = 0;                  // tile leading dimension when the beta side has no active orbitals
+};
+
 struct HostPlan {
     int n_qubits = 0, n_elec = 0, hcb = 0;
     int n = 0;         // bits per spin string (spatial orbitals)
     int k = 0;         // electrons (pairs for hcb) per string
     int64_t nstr = 0;  // strings per spin
     int64_t na = 0, nb = 0, N = 0;
-    std::vector<uint32_t> strings;  // ascending integers with k bits among n
+    std::vector<int> bitpos;        // orbital -> storage bit position
+    std::vector<uint32_t> strings;  // storage order; values are ORIGINAL occupation bits
+    std::vector<uint32_t> ref2int;  // reference address -> storage address
+    std::vector<uint32_t> int2ref;
+    bool identity_layout = true;
     std::vector<std::vector<int64_t>> binom;
     std::vector<HopTable> hops;
     std::map<uint64_t, int> hop_index;
     std::vector<OpDesc> ops;
+    std::vector<Batch> batches;
     int n_params = 0;
     std::string error;
 
     int init(int n_qubits, int n_elec, int hcb);
-    // address of a string with exactly k bits (combinatorial number system)
-    int64_t rank(uint32_t s) const;
-    // rank if popcount == k else 0 (the reference's zero-initialised lookup, ci_utils.py:27-28)
-    int64_t rank_or_zero(uint64_t s) const;
+    // validation + masks + sign; no tables (strings may not exist yet)
+    int parse_op(const int32_t* idx, int len, int param, OpDesc* op);
+    // groups ops into batches (orbital sets only), picks the storage order, builds strings, hop tables
+    // and batch descriptors.  tile_elems = max determinants per on-chip tile.
+    void finalize(int tile_elems, bool use_layout);
+    void attach_hops(OpDesc* op);
+
+    uint32_t permute_bits(uint32_t s) const;
+    int64_t colex_rank(uint32_t t) const;                  // rank of a k-subset given as bits
+    int64_t rank(uint32_t s) const { return colex_rank(permute_bits(s)); }  // storage address
+    int64_t ref_rank(uint32_t s) const { return colex_rank(s); }
+    // reference address if popcount == k else 0 (the reference's zero-initialised lookup, ci_utils.py:27-28)
+    int64_t ref_rank_or_zero(uint64_t s) const;
     int find_or_build_hop(uint32_t cre, uint32_t ann);
-    // returns 0 or a TCC_ERR_* code; fills `op`
-    int make_op(const int32_t* idx, int len, int param, OpDesc* op);
     int64_t support_pairs(const OpDesc& op) const;
-    // reference-format tables for one op (evolve_civector.py:91-106)
+    // reference-format tables for one op (evolve_civector.py:91-106), reference order
     void expand_tables(const OpDesc& op, uint64_t* perm, int8_t* phase, int8_t* f2) const;
 
-    // sigma tables (non-hcb)
+    // sigma tables (non-hcb), storage order
     int ml = 0;                // links per string padded to a multiple of 8
     std::vector<Link> links;   // [nstr, ml]
     void build_links();
-    // string-space same-spin Hamiltonian sum h2e[pq,rs] E_pq E_rs in ELL form, rows = output string
     int ell_width = 0;
     std::vector<uint32_t> ell_col;  // [nstr, ell_width]
     std::vector<double> ell_val;
     void build_same_spin_ell(const std::vector<double>& h2e);
+
+   private:
+    std::vector<std::vector<int>> group_ops(int tile_elems) const;
+    void choose_layout(const std::vector<std::vector<int>>& groups, bool use_layout);
+    void build_strings();
+    void build_batch(const std::vector<int>& group, int tile_elems, Batch* out);
+    void build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string);
+    int64_t max_class(int m) const;
 };
 
 // pyscf direct_nosym.absorb_h1e with the factor 0.5 of hamiltonian.py:148

@@ -81,6 +81,28 @@ class Plan:
         )
         return perm, phase, f2
 
+    @property
+    def n_batches(self) -> int:
+        return int(self.lib.tcc_num_batches(self.handle))
+
+    def batch_info(self, b: int) -> dict:
+        """Schedule introspection: ops of batch ``b`` (application order), active orbital counts, tile geometry."""
+        vals = [C.c_int32(0) for _ in range(6)]
+        _lib.check(self.lib.tcc_batch_info(self.handle, int(b), *[C.byref(v) for v in vals], None))
+        n_ops = vals[0].value
+        idx = np.zeros(max(n_ops, 1), dtype=np.int32)
+        _lib.check(self.lib.tcc_batch_info(self.handle, int(b), *[C.byref(v) for v in vals], idx.ctypes.data_as(C.POINTER(C.c_int32))))
+        keys = ("n_ops", "active_alpha", "active_beta", "n_tiles", "max_tile_rows", "max_tile_cols")
+        info = {k: v.value for k, v in zip(keys, vals)}
+        info["op_indices"] = idx[:n_ops].tolist()
+        return info
+
+    def storage_order(self) -> np.ndarray:
+        """ref2int: storage address of each per-spin string, indexed by its reference address."""
+        out = np.zeros(self.n_strings, dtype=np.uint32)
+        _lib.check(self.lib.tcc_storage_order(self.handle, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
     def op_support_bytes(self, j: int) -> int:
         return int(self.lib.tcc_op_support_bytes(self.handle, int(j)))
 
@@ -107,6 +129,14 @@ class Plan:
             )
         )
         return {name: (float(ms[i]), int(launches[i]), int(nbytes[i])) for i, name in enumerate(_lib.PROF_SLOTS)}
+
+    def profile_batches(self, on=True):
+        """Returns (fwd_ms, rev_ms) per batch of the last energy_and_grad call (zeros if recording was off)."""
+        fwd = np.zeros(max(self.n_batches, 1), dtype=np.float32)
+        rev = np.zeros(max(self.n_batches, 1), dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        _lib.check(self.lib.tcc_profile_batches(self.handle, int(bool(on)), fwd.ctypes.data_as(fp), rev.ctypes.data_as(fp)))
+        return fwd[: self.n_batches], rev[: self.n_batches]
 
     # ---- Hamiltonian ----
     def set_hamiltonian(self, int1e, int2e, token=None):

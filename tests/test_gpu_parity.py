@@ -281,6 +281,51 @@ def test_properties_medium_size():
     O.clear_cache()
 
 
+@pytest.mark.parametrize("tile_elems,threads", [(64, 32), (400, 64), (1500, 128), (1500, 256)])
+def test_small_tiles_many_batches(tile_elems, threads, monkeypatch):
+    """Force the batch planner into many batches / many tiles per batch (what large active spaces look like)
+    on a size the oracle can check: state, energy AND gradient (tile-partial reduction, spectator signs)."""
+    monkeypatch.setenv("TCC_B200_TILE_ELEMS", str(tile_elems))
+    monkeypatch.setenv("TCC_B200_BATCH_THREADS", str(threads))
+    clear_cache()
+    for kind, no, nv in [("uccsd", 4, 4), ("uccsd", 3, 4), ("kupccgsd", 3, 3), ("puccd", 4, 4)]:
+        ucc, int1e, int2e = _build(kind, no, nv)
+        params = _params(ucc.n_params)
+        plan = Plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, hcb=ucc.hcb)
+        plan.set_hamiltonian(int1e, int2e)
+        if kind == "uccsd" and no == 4 and tile_elems <= 400:
+            assert plan.n_batches > 2
+        h = O.get_h_from_integral(int1e, int2e, ucc.n_elec, ucc.hcb)
+        e_ref, g_ref = O.get_energy_and_grad(params, h, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb)
+        c_ref = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb)
+        e, g = plan.energy_and_grad(params)
+        assert np.abs(plan.civector(params) - c_ref).max() < C_TOL
+        assert abs(e - e_ref) < E_TOL
+        assert np.abs(g - g_ref).max() < G_TOL
+        O.clear_cache()
+    clear_cache()
+
+
+def test_batch_schedule_is_a_valid_reordering():
+    """Every excitation appears exactly once, and two excitations whose relative order changed act on disjoint
+    spin-orbitals (so their generators commute and the product of factors is unchanged)."""
+    ucc, _, _ = _build("uccsd", 4, 4)
+    for tile in (64, 400, 6144):
+        os.environ["TCC_B200_TILE_ELEMS"] = str(tile)
+        try:
+            plan = Plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, device=None)
+        finally:
+            del os.environ["TCC_B200_TILE_ELEMS"]
+        order = [j for b in range(plan.n_batches) for j in plan.batch_info(b)["op_indices"]]
+        assert sorted(order) == list(range(len(ucc.ex_ops)))
+        pos = {j: i for i, j in enumerate(order)}
+        sets = [set(op) for op in ucc.ex_ops]
+        for a in range(len(order)):
+            for b in range(a + 1, len(order)):
+                if pos[a] > pos[b]:
+                    assert not (sets[a] & sets[b]), (ucc.ex_ops[a], ucc.ex_ops[b])
+
+
 def test_device_resident_api():
     import torch
 

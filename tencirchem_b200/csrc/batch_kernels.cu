@@ -12,7 +12,7 @@
 
 namespace tcc {
 
-constexpr int BK_THREADS = 256;
+constexpr int BK_THREADS = 256;  // upper bound of the launch; the actual block size is a launch parameter
 constexpr int BK_WARPS = BK_THREADS / 32;
 constexpr int BK_DEPTH = 4;  // excitations per prefetch group
 constexpr int BK_COLCH = 4;  // tile columns per lane kept in registers (tiles up to 128 columns)
@@ -138,21 +138,31 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
     __syncthreads();  // row_addr, sops
     // ---- gather the tile
     if (reg_cols) {
-        for (int lr = warp; lr < nR; lr += nwarps) {
-            const double* src0 = v0 + int64_t(row_addr[lr]) * nb;
-            const double* src1 = NV == 2 ? v1 + int64_t(row_addr[lr]) * nb : nullptr;
-            double a[BK_COLCH], b[BK_COLCH];
+        // two rows per step: all global loads of both rows are issued before the first shared store waits on them
+        for (int lr = warp; lr < nR; lr += 2 * nwarps) {
+            const int lr2 = lr + nwarps;
+            const bool has2 = lr2 < nR;
+            const int64_t ra = int64_t(row_addr[lr]) * nb, rb = has2 ? int64_t(row_addr[lr2]) * nb : ra;
+            double a[BK_COLCH], b[BK_COLCH], c[BK_COLCH], d[BK_COLCH];
 #pragma unroll
             for (int j = 0; j < BK_COLCH; ++j)
                 if (lcs[j] >= 0) {
-                    a[j] = src0[colg[j]];
-                    if (NV == 2) b[j] = src1[colg[j]];
+                    a[j] = v0[ra + colg[j]];
+                    if (NV == 2) b[j] = v1[ra + colg[j]];
+                    if (has2) {
+                        c[j] = v0[rb + colg[j]];
+                        if (NV == 2) d[j] = v1[rb + colg[j]];
+                    }
                 }
 #pragma unroll
             for (int j = 0; j < BK_COLCH; ++j)
                 if (lcs[j] >= 0) {
                     t0[lr * ld + lcs[j]] = a[j];
                     if (NV == 2) t1[lr * ld + lcs[j]] = b[j];
+                    if (has2) {
+                        t0[lr2 * ld + lcs[j]] = c[j];
+                        if (NV == 2) t1[lr2 * ld + lcs[j]] = d[j];
+                    }
                 }
         }
     } else {

@@ -129,7 +129,8 @@ struct tcc_plan {
     BatchTimer btimer;
     int device = 0;
     int mode = 0;  // 0 = batched tiles, 1 = one launch per excitation
-    int batch_threads = 128;
+    int batch_threads = 256;      // forward batch kernel block size
+    int batch_threads_rev = 256;  // reverse batch kernel block size
     std::vector<DevHop> dhops;
     std::vector<BatchDevSet> dbatches;
     double* ket = nullptr;
@@ -343,7 +344,8 @@ int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t*
     }
     p->hp.n_params = max_param + 1;
     p->mode = env_int("TCC_B200_PER_OP", 0) ? 1 : 0;
-    p->batch_threads = std::min(256, std::max(32, env_int("TCC_B200_BATCH_THREADS", 128) / 32 * 32));
+    p->batch_threads = std::min(256, std::max(32, env_int("TCC_B200_BATCH_THREADS", 256) / 32 * 32));
+    p->batch_threads_rev = std::min(256, std::max(32, env_int("TCC_B200_BATCH_THREADS_REV", p->batch_threads) / 32 * 32));
     p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0);
     {
         uint32_t hf = p->hp.k ? ((1u << p->hp.k) - 1) : 0u;
@@ -651,7 +653,7 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
         for (int b = nbt - 1; b >= 0; --b) {
             BatchDevSet& db = p->dbatches[b];
             if (p->btimer.on) cudaEventRecord(p->btimer.ev[nbt + 1 + (nbt - 1 - b)], st);
-            launch_batch_reverse(ket, bra, hp.nb, db.rev, p->d_rot_rev, db.smem_rev, p->batch_threads, p->bpart, p->grad_ops, st);
+            launch_batch_reverse(ket, bra, hp.nb, db.rev, p->d_rot_rev, db.smem_rev, p->batch_threads_rev, p->bpart, p->grad_ops, st);
             p->prof.count(TCC_PROF_REV_BATCH, 2, 32 * hp.N);
             p->launches += 2;
         }

@@ -234,6 +234,9 @@ std::vector<std::vector<int>> HostPlan::group_ops(int tile_elems) const {
     const size_t window = 8192;
     const size_t max_ops = 256;
     const uint32_t all = n >= 32 ? 0xffffffffu : ((1u << n) - 1);
+    int64_t side_cap = 64;
+    while (side_cap * side_cap < 4 * int64_t(tile_elems)) ++side_cap;  // 2 * sqrt(tile_elems)
+    if (hcb) side_cap = tile_elems;
     while (!remaining.empty()) {
         std::vector<int> batch, rest;
         uint32_t sa = 0, sb = 0, skip_a = 0, skip_b = 0;
@@ -249,8 +252,9 @@ std::vector<std::vector<int>> HostPlan::group_ops(int tile_elems) const {
             bool blocked = (oa & skip_a) || (ob & skip_b);
             if (!blocked) {
                 uint32_t nsa = sa | oa, nsb = sb | ob;
-                int64_t elems = max_class(hcb ? 0 : popc(nsa)) * max_class(popc(nsb));
-                if (elems <= tile_elems || batch.empty()) {
+                int64_t ca = max_class(hcb ? 0 : popc(nsa)), cb = max_class(popc(nsb));
+                // keep tiles roughly square: a long thin tile has row segments too short to coalesce
+                if ((ca * cb <= tile_elems && ca <= side_cap && cb <= side_cap) || batch.empty()) {
                     batch.push_back(j);
                     sa = nsa;
                     sb = nsb;

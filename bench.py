@@ -284,7 +284,9 @@ def run_b200(args):
     kernel_names = {"rev_alphabeta": "reverse_kernel<false,false>", "rev_alpha": "reverse_kernel<false,true>",
                     "rev_beta": "reverse_kernel<true,false>", "fwd_alphabeta": "rotate_kernel<false,false>",
                     "fwd_alpha": "rotate_kernel<false,true>", "fwd_beta": "rotate_kernel<true,false>",
-                    "sigma_ab": "sigma_ab_kernel", "sigma_ss": "spmm_rows_kernel+transpose_kernel", "dot": "dot_kernel"}
+                    "sigma_ab": "sigma_ab_kernel", "sigma_ss": "spmm_rows_kernel+transpose_kernel", "dot": "dot_kernel",
+                    "fwd_batch": "batch_kernel<1> (one launch per batch of excitations, whole vector read+written once)",
+                    "rev_batch": "batch_kernel<2> (+ batch_grad_reduce_kernel; ket and bra read+written once per batch)"}
     total_prof_ms = sum(v[0] for v in prof.values())
     phases = {s: {"ms_per_step": round(v[0] / args.steps, 3), "launches_per_step": v[1] // args.steps,
                   "algorithmic_GBps": round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 else None,
@@ -297,7 +299,7 @@ def run_b200(args):
         "config": {"workload": workload_desc(n), "n_determinants": size, "n_excitations": m, "n_params": p_count,
                    "l2": "inputs larger than L2 (1.3 GB vectors vs 126 MB)" if size * 8 > 2.5e8 else "vectors fit in L2; no flush",
                    "multi_gpu": "independent theta sets per rank, no data-path collective" if world > 1 else "single GPU",
-                   "staging_s": round(staging_s, 2)},
+                   "n_batches": plan.n_batches, "staging_s": round(staging_s, 2)},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": 8 * p_count, "d2h_bytes_per_step": 8 * (m + 1),
                 "note": "public API UCCSD.energy_and_grad(params): host params in, host (energy, gradient) out; the CI vectors never leave HBM"},
         "gpu_launches": int(launches),

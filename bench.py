@@ -202,6 +202,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    torch.cuda.init()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -225,12 +226,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the public API call a user makes; it must route to the same plan (module-level plan cache)
-    import tencirchem_b200.evolve_civector as ev
-    if local_rank != 0:
-        # the ansatz classes use device 0 of the process by default; make the cached plan the rank's device
-        ev._PLAN_CACHE[(ucc.n_qubits, ucc.n_elec, tuple(tuple(o) for o in ucc.ex_ops), tuple(ucc.param_ids), False, 0)] = plan
-
+    # the public API call a user makes routes to the same cached plan (one process per GPU: torch's current device)
     for w in range(args.warmup):
         plan.energy_and_grad_dev(theta(-1 - w))
     barrier()

@@ -1,5 +1,3 @@
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
-$CMD > gpurun_out/plain_16o.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 2343 -c 800 --csv --log-file gpurun_out/launches_16o.csv $CMD > gpurun_out/ncu_l.log 2>&1
-tail -1 gpurun_out/ncu_l.log | cut -c1-200
-$CMD > gpurun_out/plain_16o.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:batch_kernel -s 1290 -c 4 -o gpurun_out/prof_final_batch_16o $CMD > gpurun_out/ncu_f.log 2>&1
-tail -1 gpurun_out/ncu_f.log | cut -c1-200
+nvidia-smi -L
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | tail -3 | cut -c1-900
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 --workload 10o 2>&1 | tail -2 | cut -c1-400

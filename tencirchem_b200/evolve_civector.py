@@ -21,7 +21,24 @@ def clear_cache():
     _PLAN_CACHE.clear()
 
 
-def get_plan(n_qubits, n_elec, ex_ops, param_ids, hcb=False, device=0) -> Plan:
+def default_device() -> int:
+    """The GPU this process computes on: TCC_B200_DEVICE, else torch's current device when torch has already
+    initialised CUDA (one process per GPU under torchrun), else device 0."""
+    import os
+    import sys
+
+    env = os.environ.get("TCC_B200_DEVICE")
+    if env is not None:
+        return int(env)
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+        return int(torch.cuda.current_device())
+    return 0
+
+
+def get_plan(n_qubits, n_elec, ex_ops, param_ids, hcb=False, device=None) -> Plan:
+    if device is None:
+        device = default_device()
     ex_ops = tuple(tuple(op) for op in ex_ops)
     if param_ids is None:
         param_ids = range(len(ex_ops))

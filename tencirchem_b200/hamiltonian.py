@@ -27,7 +27,9 @@ def _make_handle(int1e, int2e, n_elec, hcb):
 
     def fci_func(civector):
         if state["plan"] is None:
-            plan = Plan(n_qubits, n_elec, (), (), hcb=hcb)
+            from .evolve_civector import default_device
+
+            plan = Plan(n_qubits, n_elec, (), (), hcb=hcb, device=default_device())
             plan.set_hamiltonian(int1e, int2e, token=fci_func)
             state["plan"] = plan
         return state["plan"].apply_h(civector)

@@ -1,0 +1,70 @@
+"""CPU, world_size 2, gloo: the host-side logic of the multi-GPU benchmark path (small-N /
+multi-theta regime): every rank evaluates its own parameter sets, no data-path collective, timings are reduced
+with MAX over ranks and the per-rank results are gathered.  No GPU work is done here."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tencirchem_b200.parallel import reduce_timing_max, shard_parameter_sets, gather_results
+
+    thetas = np.arange(10 * 3, dtype=np.float64).reshape(10, 3)
+    mine = shard_parameter_sets(thetas, rank, world)
+    # stand-in for the GPU evaluation: a deterministic function of theta
+    energies = mine.sum(axis=1)
+    grads = 2.0 * mine
+    t = reduce_timing_max(10.0 + rank)
+    e_all, g_all = gather_results(energies, grads, n_total=len(thetas), rank=rank, world=world)
+    if rank == 0:
+        out.put((t, e_all.tolist(), g_all.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_parameter_sets_shard_and_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    t, e_all, g_all = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    thetas = np.arange(30, dtype=np.float64).reshape(10, 3)
+    assert t == 11.0  # MAX over ranks
+    np.testing.assert_array_equal(np.array(e_all), thetas.sum(axis=1))
+    np.testing.assert_array_equal(np.array(g_all), 2.0 * thetas)
+
+
+def test_shard_sizes_are_balanced():
+    sys.path.insert(0, ROOT)
+    from tencirchem_b200.parallel import shard_bounds
+
+    for n, w in [(10, 2), (7, 4), (3, 8), (1024, 8), (0, 2)]:
+        bounds = [shard_bounds(n, r, w) for r in range(w)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == n
+        sizes = [b - a for a, b in bounds]
+        assert max(sizes) - min(sizes) <= 1
+        assert all(bounds[i][1] == bounds[i + 1][0] for i in range(w - 1))

@@ -1,3 +1,3 @@
-nvidia-smi -L
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | tail -3 | cut -c1-900
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 --workload 10o 2>&1 | tail -2 | cut -c1-400
+python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+TCC_B200_PANEL_CLASSES=3 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+for g in 1 2 4; do echo "== classes $g"; TCC_B200_PANEL_CLASSES=$g python scripts/batch_times.py 16 2>&1 | tail -4 | head -3; done

@@ -17,6 +17,11 @@ constexpr int BK_WARPS = BK_THREADS / 32;
 constexpr int BK_DEPTH = 4;  // excitations per prefetch group
 constexpr int BK_COLCH = 4;  // tile columns per lane kept in registers (tiles up to 128 columns)
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+    const unsigned s = unsigned(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+
 // per-op record resolved for the tile's (e_alpha, e_beta) at kernel start
 struct SmemOp {
     int off, cnt;   // slice of the expanded pair list
@@ -138,33 +143,18 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
     __syncthreads();  // row_addr, sops
     // ---- gather the tile
     if (reg_cols) {
-        // two rows per step: all global loads of both rows are issued before the first shared store waits on them
-        for (int lr = warp; lr < nR; lr += 2 * nwarps) {
-            const int lr2 = lr + nwarps;
-            const bool has2 = lr2 < nR;
-            const int64_t ra = int64_t(row_addr[lr]) * nb, rb = has2 ? int64_t(row_addr[lr2]) * nb : ra;
-            double a[BK_COLCH], b[BK_COLCH], c[BK_COLCH], d[BK_COLCH];
+        // asynchronous global->shared copies (LDGSTS): every element of the tile is in flight before the first
+        // wait, so the gather costs about one memory latency instead of one per row
+        for (int lr = warp; lr < nR; lr += nwarps) {
+            const int64_t ra = int64_t(row_addr[lr]) * nb;
 #pragma unroll
             for (int j = 0; j < BK_COLCH; ++j)
                 if (lcs[j] >= 0) {
-                    a[j] = v0[ra + colg[j]];
-                    if (NV == 2) b[j] = v1[ra + colg[j]];
-                    if (has2) {
-                        c[j] = v0[rb + colg[j]];
-                        if (NV == 2) d[j] = v1[rb + colg[j]];
-                    }
-                }
-#pragma unroll
-            for (int j = 0; j < BK_COLCH; ++j)
-                if (lcs[j] >= 0) {
-                    t0[lr * ld + lcs[j]] = a[j];
-                    if (NV == 2) t1[lr * ld + lcs[j]] = b[j];
-                    if (has2) {
-                        t0[lr2 * ld + lcs[j]] = c[j];
-                        if (NV == 2) t1[lr2 * ld + lcs[j]] = d[j];
-                    }
+                    cp_async8(t0 + lr * ld + lcs[j], v0 + ra + colg[j]);
+                    if (NV == 2) cp_async8(t1 + lr * ld + lcs[j], v1 + ra + colg[j]);
                 }
         }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
     } else {
         for (int lr = warp; lr < nR; lr += nwarps) {
             const int64_t row = int64_t(row_addr[lr]) * nb;

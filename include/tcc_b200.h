@@ -106,6 +106,13 @@ int tcc_energy(tcc_plan* plan, const double* params_host, const double* init_dev
 int tcc_energy_and_grad(tcc_plan* plan, const double* params_host, const double* init_dev,
                         double* energy_host, double* grad_host, void* stream);
 
+/* ---- batched parameter sets (additive API; the reference accepts one theta per call and loops in Python:
+ * kupccgsd.py:98-125 multi-start, h2o_pes.ipynb cell 7).  params_host [n_sets, num_params] row-major;
+ * energies_host [n_sets]; grads_host [n_sets, num_params] or NULL (energies only).  Starts from the HF
+ * determinant.  All sets of a chunk run in the same launches (one grid dimension per set). */
+int tcc_energy_and_grad_batch(tcc_plan* plan, int n_sets, const double* params_host, double* energies_host,
+                              double* grads_host, void* stream);
+
 /* ---- G|c> for one excitation: apply_excitation_civector, evolve_civector.py:311-313 ------ */
 int tcc_apply_excitation(tcc_plan* plan, const double* c_dev, const int32_t* ex_op, int ex_op_len,
                          double* out_dev, void* stream);

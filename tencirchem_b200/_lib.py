@@ -47,6 +47,7 @@ SIGNATURES = {
     "tcc_civector": (C.c_int, [_p, _dp, _p, _p, _p]),
     "tcc_energy": (C.c_int, [_p, _dp, _p, _dp, _p]),
     "tcc_energy_and_grad": (C.c_int, [_p, _dp, _p, _dp, _dp, _p]),
+    "tcc_energy_and_grad_batch": (C.c_int, [_p, C.c_int, _dp, _dp, _dp, _p]),
     "tcc_apply_excitation": (C.c_int, [_p, _p, _ip, C.c_int, _p, _p]),
     "tcc_civector_host": (C.c_int, [_p, _dp, _dp, _dp]),
     "tcc_apply_h_host": (C.c_int, [_p, _dp, _dp]),

@@ -84,8 +84,13 @@ __device__ __forceinline__ double rotate_pairs(double* __restrict__ t0, double* 
 template <int NV>
 __global__ void __launch_bounds__(BK_THREADS)
 batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, BatchDev bd, const double2* __restrict__ rot,
-             double* __restrict__ partials, int n_tiles) {
+             double* __restrict__ partials, int n_tiles, SetStrides ss) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // blockIdx.y = parameter set (batched-theta evaluation): own vectors, angles and gradient partials
+    v0 += int64_t(blockIdx.y) * ss.vec;
+    if (NV == 2) v1 += int64_t(blockIdx.y) * ss.vec;
+    rot += int64_t(blockIdx.y) * ss.rot;
+    if (NV == 2) partials += int64_t(blockIdx.y) * ss.part;
     const int tile_id = blockIdx.x;
     const int pa_id = tile_id / bd.B.n_panels;
     const PanelDesc pa = bd.A.panels[pa_id];
@@ -303,8 +308,11 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
 
 // grad_ops[op_index] = s0 * sum over tiles of partials[t, :], fixed order
 __global__ void __launch_bounds__(256) batch_grad_reduce_kernel(const double* __restrict__ partials, int n_tiles,
-                                                                const BatchOp* __restrict__ ops, double* __restrict__ grad_ops) {
+                                                                const BatchOp* __restrict__ ops, double* __restrict__ grad_ops,
+                                                                SetStrides ss) {
     __shared__ double wsum[8];
+    partials += int64_t(blockIdx.y) * ss.part;
+    grad_ops += int64_t(blockIdx.y) * ss.grad;
     const int t = blockIdx.x;
     const double* row = partials + int64_t(t) * n_tiles;
     double s = 0.0;
@@ -335,17 +343,17 @@ cudaError_t batch_kernels_configure() {
 }
 
 void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem, int threads,
-                          cudaStream_t st) {
-    dim3 grid(unsigned(bd.B.n_panels) * unsigned(bd.A.n_panels), 1, 1);
-    batch_kernel<1><<<grid, threads, smem, st>>>(v, nullptr, nb, bd, rot, nullptr, 0);
+                          int n_sets, SetStrides ss, cudaStream_t st) {
+    dim3 grid(unsigned(bd.B.n_panels) * unsigned(bd.A.n_panels), unsigned(n_sets), 1);
+    batch_kernel<1><<<grid, threads, smem, st>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss);
 }
 
 void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem,
-                          int threads, double* partials, double* grad_ops, cudaStream_t st) {
-    dim3 grid(unsigned(bd.B.n_panels) * unsigned(bd.A.n_panels), 1, 1);
+                          int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st) {
+    dim3 grid(unsigned(bd.B.n_panels) * unsigned(bd.A.n_panels), unsigned(n_sets), 1);
     const int n_tiles = bd.B.n_panels * bd.A.n_panels;
-    batch_kernel<2><<<grid, threads, smem, st>>>(ket, bra, nb, bd, rot, partials, n_tiles);
-    batch_grad_reduce_kernel<<<bd.nops, 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops);
+    batch_kernel<2><<<grid, threads, smem, st>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss);
+    batch_grad_reduce_kernel<<<dim3(bd.nops, unsigned(n_sets), 1), 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops, ss);
 }
 
 // out[a, b] = in[map_a[a], map_b[b]]  (storage order <-> reference order)

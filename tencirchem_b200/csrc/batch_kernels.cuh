@@ -31,12 +31,20 @@ struct BatchDev {
     int reversed;  // ops[] is the forward list reversed
 };
 
+// element strides between consecutive parameter sets of a batched-theta evaluation (all 0 for a single set)
+struct SetStrides {
+    int64_t vec;   // CI vectors
+    int64_t rot;   // (cos, sin) records
+    int64_t part;  // per-tile gradient partials
+    int64_t grad;  // per-excitation gradients
+};
+
 cudaError_t batch_kernels_configure();
 size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv);
 void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem, int threads,
-                          cudaStream_t st);
+                          int n_sets, SetStrides ss, cudaStream_t st);
 void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem,
-                          int threads, double* partials, double* grad_ops, cudaStream_t st);
+                          int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st);
 void launch_permute(const double* in, double* out, int64_t na, int64_t nb, const uint32_t* map_a, const uint32_t* map_b,
                     cudaStream_t st);
 

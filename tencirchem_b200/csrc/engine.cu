@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -214,6 +215,11 @@ static int upload_side(tcc_plan* p, const SideBatch& s, SideDev* d, std::vector<
     return 0;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
 static int upload_batches(tcc_plan* p) {
     HostPlan& hp = p->hp;
     p->dbatches.resize(hp.batches.size());
@@ -236,7 +242,7 @@ static int upload_batches(tcc_plan* p) {
         db.n_tiles = db.fwd.A.n_panels * db.fwd.B.n_panels;
         db.max_rows = hb.A.max_panel;
         db.max_cols = hb.B.max_panel;
-        db.smem_fwd = batch_smem_bytes(hb.A.max_panel, hb.B.max_panel, db.nops, 1);
+        db.smem_fwd = batch_smem_bytes(hb.A.max_panel, hb.B.max_panel, db.nops, 1) + size_t(env_int("TCC_B200_EXTRA_SMEM_KB", 0)) * 1024;
         db.smem_rev = batch_smem_bytes(hb.A.max_panel, hb.B.max_panel, db.nops, 2);
         if (db.smem_rev > 232448)
             return fail(TCC_ERR_BAD_ARGUMENT, "batch tile does not fit in shared memory: lower TCC_B200_TILE_ELEMS");
@@ -271,10 +277,6 @@ static int use_device(const tcc_plan* p) {
     return 0;
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* v = std::getenv(name);
-    return (v && *v) ? std::atoi(v) : dflt;
-}
 
 // reference order -> storage order and back (vectors crossing the ABI are in reference order)
 static void to_storage(tcc_plan* p, const double* ref, double* st_vec, cudaStream_t st) {
@@ -398,8 +400,14 @@ int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t*
     return 0;
 }
 
+static void free_sets_ws(tcc_plan* p);
+
 void tcc_plan_destroy(tcc_plan* p) {
     if (!p) return;
+    if (p->device >= 0) {
+        cudaSetDevice(p->device);
+        free_sets_ws(p);
+    }
     if (p->device < 0) {
         delete p;
         return;
@@ -555,32 +563,40 @@ int tcc_set_hamiltonian(tcc_plan* p, const double* int1e, const double* int2e) {
     return 0;
 }
 
-static int apply_h_impl(tcc_plan* p, const double* c, double* sigma, cudaStream_t st) {
+// sigma = H c for n_sets vectors stored back to back (storage order); ws1 / ws2: scratch of the same size
+static int apply_h_sets(tcc_plan* p, const double* c, double* sigma, double* ws1, double* ws2, int n_sets, cudaStream_t st) {
     HostPlan& hp = p->hp;
     if (!p->has_h) return fail(TCC_ERR_NO_HAMILTONIAN, "tcc_set_hamiltonian has not been called");
     if (hp.hcb) {
-        launch_sigma_hcb(c, sigma, hp.nstr, p->d_strings, hp.n, hp.k, p->d_diag1, p->d_hop, p->d_diag2, p->d_binom, hp.n + 2, p->d_bitpos, st);
+        launch_sigma_hcb(c, sigma, hp.nstr, p->d_strings, hp.n, hp.k, p->d_diag1, p->d_hop, p->d_diag2, p->d_binom, hp.n + 2,
+                         p->d_bitpos, n_sets, st);
         p->launches += 1;
         return 0;
     }
-    if (int rc = ensure_vec(p, &p->ws1)) return rc;
-    if (int rc = ensure_vec(p, &p->ws2)) return rc;
-    const int64_t vec = hp.N * 8;
+    const int64_t vec = hp.N * 8 * n_sets;
     // alpha-alpha: sigma(a', :) = sum_a Hss[a', a] c(a, :)
     p->prof.mark(TCC_PROF_SIGMA_SS, st);
-    launch_spmm_rows(c, sigma, hp.na, hp.nb, p->d_ell_col, p->d_ell_val, hp.ell_width, false, st);
+    launch_spmm_rows(c, sigma, hp.na, hp.nb, p->d_ell_col, p->d_ell_val, hp.ell_width, false, n_sets, st);
     // beta-beta on the transposed matrix, then added back transposed
-    launch_transpose(c, p->ws1, hp.na, hp.nb, false, st);
-    launch_spmm_rows(p->ws1, p->ws2, hp.nb, hp.na, p->d_ell_col, p->d_ell_val, hp.ell_width, false, st);
-    launch_transpose(p->ws2, sigma, hp.nb, hp.na, true, st);
+    launch_transpose(c, ws1, hp.na, hp.nb, false, n_sets, st);
+    launch_spmm_rows(ws1, ws2, hp.nb, hp.na, p->d_ell_col, p->d_ell_val, hp.ell_width, false, n_sets, st);
+    launch_transpose(ws2, sigma, hp.nb, hp.na, true, n_sets, st);
     p->prof.count(TCC_PROF_SIGMA_SS, 4, 9 * vec);  // 2+2+2+3 vector passes
     // alpha-beta on the FP64 tensor path
     p->prof.mark(TCC_PROF_SIGMA_AB, st);
-    launch_sigma_ab(c, sigma, hp.na, hp.nb, p->d_links, hp.ml, p->d_w, hp.n, p->n2p, st);
+    launch_sigma_ab(c, sigma, hp.na, hp.nb, p->d_links, hp.ml, p->d_w, hp.n, p->n2p, n_sets, st);
     p->prof.count(TCC_PROF_SIGMA_AB, (hp.na + 65534) / 65535, 3 * vec);
     p->prof.mark(-1, st);
     p->launches += 4 + (hp.na + 65534) / 65535;
     return 0;
+}
+
+static int apply_h_impl(tcc_plan* p, const double* c, double* sigma, cudaStream_t st) {
+    if (!p->hp.hcb) {
+        if (int rc = ensure_vec(p, &p->ws1)) return rc;
+        if (int rc = ensure_vec(p, &p->ws2)) return rc;
+    }
+    return apply_h_sets(p, c, sigma, p->ws1, p->ws2, 1, st);
 }
 
 // ---- sweeps on storage-order vectors ------------------------------------------------------------
@@ -631,7 +647,7 @@ static int forward_sweep(tcc_plan* p, const double* params, double* vec, cudaStr
         for (size_t b = 0; b < nbt; ++b) {
             BatchDevSet& db = p->dbatches[b];
             if (p->btimer.on) cudaEventRecord(p->btimer.ev[b], st);
-            launch_batch_forward(vec, hp.nb, db.fwd, p->d_rot_fwd, db.smem_fwd, p->batch_threads, st);
+            launch_batch_forward(vec, hp.nb, db.fwd, p->d_rot_fwd, db.smem_fwd, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st);
             p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * hp.N);
             p->launches += 1;
         }
@@ -653,7 +669,8 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
         for (int b = nbt - 1; b >= 0; --b) {
             BatchDevSet& db = p->dbatches[b];
             if (p->btimer.on) cudaEventRecord(p->btimer.ev[nbt + 1 + (nbt - 1 - b)], st);
-            launch_batch_reverse(ket, bra, hp.nb, db.rev, p->d_rot_rev, db.smem_rev, p->batch_threads_rev, p->bpart, p->grad_ops, st);
+            launch_batch_reverse(ket, bra, hp.nb, db.rev, p->d_rot_rev, db.smem_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
+                                 SetStrides{0, 0, 0, 0}, st);
             p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * hp.N);  // the tiny gradient-reduce launch rides along
             p->launches += 2;
         }
@@ -669,7 +686,7 @@ static int prepare_state(tcc_plan* p, const double* params, const double* init_r
     if (init_ref_dev) {
         to_storage(p, init_ref_dev, vec, st);
     } else {
-        launch_set_unit(vec, hp.N, p->hf_index, st);
+        launch_set_unit(vec, hp.N, p->hf_index, 1, st);
         p->launches += 1;
     }
     return forward_sweep(p, params, vec, st);
@@ -783,6 +800,123 @@ int tcc_energy_and_grad(tcc_plan* p, const double* params_host, const double* in
     if (!p || !energy_host || !grad_host || (!params_host && p->hp.n_params > 0)) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
     return energy_impl(p, params_host, init_dev, energy_host, grad_host, cudaStream_t(stream));
+}
+
+// Batched-theta evaluation (API gap i): n_sets parameter vectors evaluated together, one
+// grid dimension per set; the CI vectors of all sets of a chunk are resident at once.
+struct SetsWorkspace {
+    int cap = 0;
+    double *ket = nullptr, *bra = nullptr, *ws1 = nullptr, *ws2 = nullptr, *grad = nullptr, *bpart = nullptr;
+    double2 *rot_fwd = nullptr, *rot_rev = nullptr, *h_rot = nullptr;
+    double* h_grad = nullptr;
+};
+static std::map<tcc_plan*, SetsWorkspace> g_sets_ws;
+
+static void free_sets_ws(tcc_plan* p) {
+    auto it = g_sets_ws.find(p);
+    if (it == g_sets_ws.end()) return;
+    SetsWorkspace& w = it->second;
+    cudaFree(w.ket);
+    cudaFree(w.bra);
+    cudaFree(w.ws1);
+    cudaFree(w.ws2);
+    cudaFree(w.grad);
+    cudaFree(w.bpart);
+    cudaFree(w.rot_fwd);
+    cudaFree(w.rot_rev);
+    if (w.h_rot) cudaFreeHost(w.h_rot);
+    if (w.h_grad) cudaFreeHost(w.h_grad);
+    g_sets_ws.erase(it);
+}
+
+int tcc_energy_and_grad_batch(tcc_plan* p, int n_sets, const double* params_host, double* energies_host, double* grads_host,
+                              void* stream) {
+    if (!p || n_sets < 0 || !energies_host || (!params_host && p->hp.n_params > 0 && n_sets > 0))
+        return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    HostPlan& hp = p->hp;
+    if (!p->has_h) return fail(TCC_ERR_NO_HAMILTONIAN, "tcc_set_hamiltonian has not been called");
+    if (n_sets == 0) return 0;
+    cudaStream_t st = cudaStream_t(stream);
+    const int m = int(hp.ops.size()), np_ = hp.n_params;
+    size_t max_part = 1;
+    for (auto& db : p->dbatches) max_part = std::max(max_part, size_t(db.nops) * size_t(db.n_tiles));
+    // chunk size: all vectors of a chunk are resident (4 vectors per set) within the memory budget
+    const double budget = double(env_int("TCC_B200_BATCH_MEM_MB", 24576)) * 1048576.0;
+    const double per_set = 4.0 * double(hp.N) * 8 + double(max_part) * 8 + double(m + 1) * 8 * 5;
+    int cap = int(std::max(1.0, std::min(double(std::min(n_sets, 8192)), budget / per_set)));
+    SetsWorkspace& w = g_sets_ws[p];
+    if (w.cap < cap) {
+        tcc_plan* key = p;
+        SetsWorkspace old = w;
+        (void)old;
+        free_sets_ws(key);
+        SetsWorkspace& nw = g_sets_ws[p];
+        const size_t vec = size_t(hp.N) * cap;
+        if (cudaMalloc(&nw.ket, vec * 8) != cudaSuccess || cudaMalloc(&nw.bra, vec * 8) != cudaSuccess ||
+            cudaMalloc(&nw.ws1, vec * 8) != cudaSuccess || cudaMalloc(&nw.ws2, vec * 8) != cudaSuccess ||
+            cudaMalloc(&nw.grad, size_t(cap) * (m + 1) * 8) != cudaSuccess || cudaMalloc(&nw.bpart, max_part * cap * 8) != cudaSuccess ||
+            cudaMalloc(&nw.rot_fwd, size_t(cap) * (m + 1) * sizeof(double2)) != cudaSuccess ||
+            cudaMalloc(&nw.rot_rev, size_t(cap) * (m + 1) * sizeof(double2)) != cudaSuccess ||
+            cudaMallocHost(&nw.h_rot, size_t(cap) * (m + 1) * 2 * sizeof(double2)) != cudaSuccess ||
+            cudaMallocHost(&nw.h_grad, size_t(cap) * (m + 1) * 8) != cudaSuccess) {
+            free_sets_ws(p);
+            return fail(TCC_ERR_CUDA, std::string("batched workspace allocation: ") + cudaGetErrorString(cudaGetLastError()));
+        }
+        nw.cap = cap;
+    }
+    SetsWorkspace& ws = g_sets_ws[p];
+    cap = ws.cap;
+    for (int s0 = 0; s0 < n_sets; s0 += cap) {
+        const int ns = std::min(cap, n_sets - s0);
+        double2* hf = ws.h_rot;
+        double2* hr = ws.h_rot + size_t(cap) * (m + 1);
+        for (int s = 0; s < ns; ++s) {
+            const double* prm = params_host + size_t(s0 + s) * np_;
+            for (int j = 0; j < m; ++j) {
+                const double th = prm[hp.ops[j].param];
+                const double c = std::cos(th), sn = std::sin(th) * hp.ops[j].s0;
+                hf[size_t(s) * m + j] = make_double2(c, sn);
+                hr[size_t(s) * m + j] = make_double2(c, -sn);
+            }
+        }
+        if (m > 0) {
+            CUDA_TRY(cudaMemcpyAsync(ws.rot_fwd, hf, sizeof(double2) * size_t(ns) * m, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(ws.rot_rev, hr, sizeof(double2) * size_t(ns) * m, cudaMemcpyHostToDevice, st));
+        }
+        launch_set_unit(ws.ket, hp.N, p->hf_index, ns, st);
+        p->launches += 1;
+        for (auto& db : p->dbatches) {
+            launch_batch_forward(ws.ket, hp.nb, db.fwd, ws.rot_fwd, db.smem_fwd, p->batch_threads, ns,
+                                 SetStrides{hp.N, m, 0, 0}, st);
+            p->launches += 1;
+        }
+        if (int rc = apply_h_sets(p, ws.ket, ws.bra, ws.ws1, ws.ws2, ns, st)) return rc;
+        launch_dot_sets(ws.bra, ws.ket, hp.N, ns, ws.grad + m, m + 1, st);
+        p->launches += 1;
+        if (grads_host) {
+            for (int b = int(p->dbatches.size()) - 1; b >= 0; --b) {
+                BatchDevSet& db = p->dbatches[b];
+                launch_batch_reverse(ws.ket, ws.bra, hp.nb, db.rev, ws.rot_rev, db.smem_rev, p->batch_threads_rev, ws.bpart, ws.grad, ns,
+                                     SetStrides{hp.N, m, int64_t(max_part), m + 1}, st);
+                p->launches += 2;
+            }
+        }
+        CUDA_TRY(cudaMemcpyAsync(ws.h_grad, ws.grad, sizeof(double) * size_t(ns) * (m + 1), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+        for (int s = 0; s < ns; ++s) {
+            const double* g = ws.h_grad + size_t(s) * (m + 1);
+            energies_host[s0 + s] = g[m];
+            if (grads_host) {
+                double* out = grads_host + size_t(s0 + s) * np_;
+                for (int i = 0; i < np_; ++i) out[i] = 0.0;
+                for (int j = 0; j < m; ++j) out[hp.ops[j].param] += g[j];
+                for (int i = 0; i < np_; ++i) out[i] *= 2.0;
+            }
+        }
+    }
+    return 0;
 }
 
 int tcc_apply_excitation(tcc_plan* p, const double* c_dev, const int32_t* ex_op, int ex_op_len, double* out_dev, void* stream) {

@@ -242,15 +242,31 @@ void launch_apply_g(const double* c, double* out, int64_t nb, SideList rows, Sid
 // vector utilities
 // ------------------------------------------------------------------------------------------------
 __global__ void set_unit_kernel(double* c, int64_t n, int64_t one_at) {
+    c += int64_t(blockIdx.y) * n;  // one vector per parameter set
     int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (; i < n; i += stride) c[i] = (i == one_at) ? 1.0 : 0.0;
 }
 
-void launch_set_unit(double* c, int64_t n, int64_t one_at, cudaStream_t st) {
+void launch_set_unit(double* c, int64_t n, int64_t one_at, int n_sets, cudaStream_t st) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    set_unit_kernel<<<unsigned(blocks), 256, 0, st>>>(c, n, one_at);
+    set_unit_kernel<<<dim3(unsigned(blocks), unsigned(n_sets), 1), 256, 0, st>>>(c, n, one_at);
+}
+
+// one CTA per parameter set: out[set * out_stride] = <x_set | y_set>  (vectors of the small-N regime)
+__global__ void __launch_bounds__(256) dot_sets_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                                                       double* __restrict__ out, int64_t out_stride) {
+    const double* xs = x + int64_t(blockIdx.x) * n;
+    const double* ys = y + int64_t(blockIdx.x) * n;
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) a += xs[i] * ys[i];
+    a = block_sum(a);
+    if (threadIdx.x == 0) out[int64_t(blockIdx.x) * out_stride] = a;
+}
+
+void launch_dot_sets(const double* x, const double* y, int64_t n, int n_sets, double* out, int64_t out_stride, cudaStream_t st) {
+    dot_sets_kernel<<<unsigned(n_sets), 256, 0, st>>>(x, y, n, out, out_stride);
 }
 
 __global__ void __launch_bounds__(256) dot_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
@@ -277,6 +293,8 @@ void launch_dot(const double* x, const double* y, int64_t n, double* partials, u
 template <bool ACC>
 __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t rows, int64_t cols) {
     __shared__ double tile[32][33];
+    in += int64_t(blockIdx.z) * rows * cols;
+    out += int64_t(blockIdx.z) * rows * cols;
     int64_t c0 = int64_t(blockIdx.x) * 32, r0 = int64_t(blockIdx.y) * 32;
     int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
@@ -298,8 +316,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
     }
 }
 
-void launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, bool accumulate, cudaStream_t st) {
-    dim3 grid(unsigned((cols + 31) / 32), unsigned((rows + 31) / 32), 1);
+void launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, bool accumulate, int n_sets, cudaStream_t st) {
+    dim3 grid(unsigned((cols + 31) / 32), unsigned((rows + 31) / 32), unsigned(n_sets));
     if (accumulate)
         transpose_kernel<true><<<grid, 256, 0, st>>>(in, out, rows, cols);
     else
@@ -319,6 +337,8 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const double* __restrict
                                                         const double* __restrict__ ell_val, int width) {
     __shared__ uint32_t s_col[SPMM_CHUNK];
     __shared__ double s_val[SPMM_CHUNK];
+    in += int64_t(blockIdx.z) * nrows * ncols;
+    out += int64_t(blockIdx.z) * nrows * ncols;
     int64_t r = blockIdx.x;
     int64_t c0 = int64_t(blockIdx.y) * 512 + threadIdx.x, c1 = c0 + 256;
     bool ok0 = c0 < ncols, ok1 = c1 < ncols;
@@ -344,8 +364,8 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const double* __restrict
 }
 
 void launch_spmm_rows(const double* in, double* out, int64_t nrows, int64_t ncols, const uint32_t* ell_col,
-                      const double* ell_val, int width, bool accumulate, cudaStream_t st) {
-    dim3 grid(unsigned(nrows), unsigned((ncols + 511) / 512), 1);
+                      const double* ell_val, int width, bool accumulate, int n_sets, cudaStream_t st) {
+    dim3 grid(unsigned(nrows), unsigned((ncols + 511) / 512), unsigned(n_sets));
     if (accumulate)
         spmm_rows_kernel<true><<<grid, 256, 0, st>>>(in, out, nrows, ncols, ell_col, ell_val, width);
     else
@@ -371,10 +391,12 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 
 __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict__ sigma, int64_t nb,
                                 const Link* __restrict__ links, int ml, const double* __restrict__ w, int n, int n2p,
-                                int64_t row0) {
+                                int64_t row0, int64_t set_stride) {
     extern __shared__ double dsm[];  // [n2p][SAB_LD]
     const int64_t a = row0 + blockIdx.y;
     const int64_t b0 = int64_t(blockIdx.x) * SAB_T;
+    c += int64_t(blockIdx.z) * set_stride;
+    sigma += int64_t(blockIdx.z) * set_stride;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     for (int i = tid; i < n2p * SAB_LD; i += nthreads) dsm[i] = 0.0;
     __syncthreads();
@@ -424,7 +446,7 @@ __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict
 }
 
 void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, const Link* links, int ml, const double* w,
-                     int n, int n2p, cudaStream_t st) {
+                     int n, int n2p, int n_sets, cudaStream_t st) {
     int units = (ml / 8) * (SAB_T / 16);
     int best_nw = 4;
     double best_eff = 0.0;
@@ -447,7 +469,7 @@ void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, con
     // grid.y is limited to 65535: launch in row batches
     for (int64_t r0 = 0; r0 < gy_total; r0 += 65535) {
         unsigned gy = unsigned(gy_total - r0 < 65535 ? gy_total - r0 : 65535);
-        sigma_ab_kernel<<<dim3(gx, gy, 1), best_nw * 32, smem, st>>>(c, sigma, nb, links, ml, w, n, n2p, r0);
+        sigma_ab_kernel<<<dim3(gx, gy, unsigned(n_sets)), best_nw * 32, smem, st>>>(c, sigma, nb, links, ml, w, n, n2p, r0, na * nb);
     }
 }
 
@@ -460,6 +482,8 @@ __global__ void sigma_hcb_kernel(const double* __restrict__ c, double* __restric
                                  const int64_t* __restrict__ binom, int binom_ld, const int* __restrict__ bitpos) {
     int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nstr) return;
+    c += int64_t(blockIdx.y) * nstr;
+    sigma += int64_t(blockIdx.y) * nstr;
     uint32_t s = strings[i];
     double ci = c[i], acc = 0.0;
     for (int p = 0; p < n; ++p) {
@@ -489,10 +513,10 @@ __global__ void sigma_hcb_kernel(const double* __restrict__ c, double* __restric
 
 void launch_sigma_hcb(const double* c, double* sigma, int64_t nstr, const uint32_t* strings, int n, int k,
                       const double* diag1, const double* hop, const double* diag2, const int64_t* binom, int binom_ld,
-                      const int* bitpos, cudaStream_t st) {
+                      const int* bitpos, int n_sets, cudaStream_t st) {
     (void)k;
     unsigned blocks = unsigned((nstr + 127) / 128);
-    sigma_hcb_kernel<<<blocks, 128, 0, st>>>(c, sigma, nstr, strings, n, diag1, hop, diag2, binom, binom_ld, bitpos);
+    sigma_hcb_kernel<<<dim3(blocks, unsigned(n_sets), 1), 128, 0, st>>>(c, sigma, nstr, strings, n, diag1, hop, diag2, binom, binom_ld, bitpos);
 }
 
 }  // namespace tcc

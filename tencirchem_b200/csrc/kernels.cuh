@@ -28,21 +28,22 @@ void launch_apply_g(const double* c, double* out, int64_t nb, SideList rows, Sid
                     cudaStream_t st);
 int reverse_partials_capacity();
 
-void launch_set_unit(double* c, int64_t n, int64_t one_at, cudaStream_t st);
+void launch_set_unit(double* c, int64_t n, int64_t one_at, int n_sets, cudaStream_t st);
+void launch_dot_sets(const double* x, const double* y, int64_t n, int n_sets, double* out, int64_t out_stride, cudaStream_t st);
 // deterministic dot product: out[0] = sum x*y
 void launch_dot(const double* x, const double* y, int64_t n, double* partials, unsigned* ticket,
                 double* out, cudaStream_t st);
-void launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, bool accumulate,
+void launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, bool accumulate, int n_sets,
                       cudaStream_t st);
 // out[r, :] (+)= sum_j val[r, j] * in[col[r, j], :]   (ELL rows, dense row vectors of length ncols)
 void launch_spmm_rows(const double* in, double* out, int64_t nrows, int64_t ncols, const uint32_t* ell_col,
-                      const double* ell_val, int width, bool accumulate, cudaStream_t st);
+                      const double* ell_val, int width, bool accumulate, int n_sets, cudaStream_t st);
 // sigma(a', b') += sum_{pq,rs} W[pq,rs] <a'|E_pq|a><b'|E_rs|b> c(a,b)  (opposite-spin part, DMMA)
 void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, const Link* links, int ml,
-                     const double* w, int n, int n2p, cudaStream_t st);
+                     const double* w, int n, int n2p, int n_sets, cudaStream_t st);
 // hard-core-boson sigma (hamiltonian.py:158-183)
 void launch_sigma_hcb(const double* c, double* sigma, int64_t nstr, const uint32_t* strings, int n, int k,
                       const double* diag1, const double* hop, const double* diag2, const int64_t* binom,
-                      int binom_ld, const int* bitpos, cudaStream_t st);
+                      int binom_ld, const int* bitpos, int n_sets, cudaStream_t st);
 
 }  // namespace tcc

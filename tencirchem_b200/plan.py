@@ -194,6 +194,21 @@ class Plan:
         g[: self.n_params] = grad[: self.n_params]
         return float(e.value), g
 
+    def energy_and_grad_batch(self, thetas, with_grad=True):
+        """Evaluate many parameter sets in the same launches (thetas [n_sets, n_params]); returns
+        (energies [n_sets], grads [n_sets, n_params] or None)."""
+        thetas = np.ascontiguousarray(np.asarray(thetas, dtype=np.float64))
+        if thetas.ndim != 2 or thetas.shape[1] < self.n_params:
+            raise ValueError(f"Incompatible parameter shape. (n_sets, {self.n_params}) is desired. Got {thetas.shape}")
+        thetas = np.ascontiguousarray(thetas[:, : self.n_params])
+        n_sets = len(thetas)
+        energies = np.zeros(n_sets, dtype=np.float64)
+        grads = np.zeros((n_sets, max(self.n_params, 1)), dtype=np.float64) if with_grad else None
+        _lib.check(
+            self.lib.tcc_energy_and_grad_batch(self.handle, n_sets, _dptr(thetas), _dptr(energies), _dptr(grads) if with_grad else None, None)
+        )
+        return energies, (grads[:, : self.n_params] if with_grad else None)
+
     def apply_excitation(self, civector, ex_op) -> np.ndarray:
         c = self._check_state(civector, "civector")
         op = np.asarray(ex_op, dtype=np.int32)

@@ -326,6 +326,44 @@ def test_batch_schedule_is_a_valid_reordering():
                     assert not (sets[a] & sets[b]), (ucc.ex_ops[a], ucc.ex_ops[b])
 
 
+@pytest.mark.parametrize("kind,no,nv", [("uccsd", 2, 2), ("uccsd", 3, 3), ("kupccgsd", 3, 2), ("puccd", 3, 3), ("uccsd", 4, 4)])
+def test_batched_parameter_sets(kind, no, nv):
+    """energy_and_grad_batch (many theta in the same launches) == one call per theta == oracle."""
+    ucc, int1e, int2e = _build(kind, no, nv)
+    plan = Plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, hcb=ucc.hcb)
+    plan.set_hamiltonian(int1e, int2e)
+    rng = np.random.default_rng(11)
+    thetas = rng.random((7, ucc.n_params)) - 0.5
+    e_b, g_b = plan.energy_and_grad_batch(thetas)
+    e_only, none = plan.energy_and_grad_batch(thetas, with_grad=False)
+    assert none is None
+    h = O.get_h_from_integral(int1e, int2e, ucc.n_elec, ucc.hcb)
+    for i, th in enumerate(thetas):
+        e1, g1 = plan.energy_and_grad(th)
+        assert abs(e_b[i] - e1) < 1e-12 and np.abs(g_b[i] - g1).max() < 1e-12
+        assert abs(e_only[i] - e1) < 1e-12
+        if i < 2:
+            e_ref, g_ref = O.get_energy_and_grad(th, h, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb)
+            assert abs(e_b[i] - e_ref) < E_TOL and np.abs(g_b[i] - g_ref).max() < G_TOL
+    O.clear_cache()
+    with pytest.raises(ValueError, match="Incompatible parameter shape"):
+        plan.energy_and_grad_batch(np.zeros((3, max(ucc.n_params - 1, 0))))
+
+
+def test_batched_parameter_sets_chunking(monkeypatch):
+    """More sets than fit the memory budget at once are processed in chunks."""
+    monkeypatch.setenv("TCC_B200_BATCH_MEM_MB", "1")
+    ucc, int1e, int2e = _build("uccsd", 3, 3)
+    plan = Plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids)
+    plan.set_hamiltonian(int1e, int2e)
+    rng = np.random.default_rng(12)
+    thetas = rng.random((50, ucc.n_params)) - 0.5
+    e_b, g_b = plan.energy_and_grad_batch(thetas)
+    for i in (0, 17, 49):
+        e1, g1 = plan.energy_and_grad(thetas[i])
+        assert abs(e_b[i] - e1) < 1e-12 and np.abs(g_b[i] - g1).max() < 1e-12
+
+
 def test_device_resident_api():
     import torch
 

@@ -218,7 +218,7 @@ def run_b200(args):
     staging_s = time.perf_counter() - t0
 
     def theta(step):
-        np.random.seed(2077 + step + 1000 * rank)
+        np.random.seed((2077 + step + 1000003 * rank) % (2**32))
         return np.random.rand(p_count) - 0.5
 
     def barrier():

@@ -84,17 +84,21 @@ __device__ __forceinline__ double rotate_pairs(double* __restrict__ t0, double* 
 template <int NV>
 __global__ void __launch_bounds__(BK_THREADS)
 batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, BatchDev bd, const double2* __restrict__ rot,
-             double* __restrict__ partials, int n_tiles, SetStrides ss) {
+             double* __restrict__ partials, int n_tiles, SetStrides ss, TileRect rect) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // blockIdx.y = parameter set (batched-theta evaluation): own vectors, angles and gradient partials
     v0 += int64_t(blockIdx.y) * ss.vec;
     if (NV == 2) v1 += int64_t(blockIdx.y) * ss.vec;
     rot += int64_t(blockIdx.y) * ss.rot;
     if (NV == 2) partials += int64_t(blockIdx.y) * ss.part;
-    const int tile_id = blockIdx.x;
-    const int pa_id = tile_id / bd.B.n_panels;
+    // this launch covers the rectangle [pa_lo, pa_lo + ..) x [pb_lo, pb_lo + pb_cnt) of the panel grid (tiles of
+    // similar size share a launch so that the shared-memory request, hence the occupancy, fits them)
+    const int pa_loc = blockIdx.x / rect.pb_cnt;
+    const int pa_id = rect.pa_lo + pa_loc;
+    const int pb_id = rect.pb_lo + (blockIdx.x - pa_loc * rect.pb_cnt);
+    const int tile_id = pa_id * bd.B.n_panels + pb_id;
     const PanelDesc pa = bd.A.panels[pa_id];
-    const PanelDesc pb = bd.B.panels[tile_id - pa_id * bd.B.n_panels];
+    const PanelDesc pb = bd.B.panels[pb_id];
     // an active side has one class per panel (G == 1); a side without active orbitals packs G single-string
     // classes, none of which is ever paired
     const int nR = int(pa.G) * int(pa.c), nC = int(pb.G) * int(pb.c);
@@ -342,17 +346,22 @@ cudaError_t batch_kernels_configure() {
     return cudaFuncSetAttribute(batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
-void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem, int threads,
-                          int n_sets, SetStrides ss, cudaStream_t st) {
-    dim3 grid(unsigned(bd.B.n_panels) * unsigned(bd.A.n_panels), unsigned(n_sets), 1);
-    batch_kernel<1><<<grid, threads, smem, st>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss);
+void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
+                          int threads, int n_sets, SetStrides ss, cudaStream_t st) {
+    for (const TileRect& r : rects) {
+        dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
+        batch_kernel<1><<<grid, threads, r.smem_fwd, st>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss, r);
+    }
 }
 
-void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem,
-                          int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st) {
-    dim3 grid(unsigned(bd.B.n_panels) * unsigned(bd.A.n_panels), unsigned(n_sets), 1);
+void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot,
+                          const std::vector<TileRect>& rects, int threads, double* partials, double* grad_ops, int n_sets,
+                          SetStrides ss, cudaStream_t st) {
     const int n_tiles = bd.B.n_panels * bd.A.n_panels;
-    batch_kernel<2><<<grid, threads, smem, st>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss);
+    for (const TileRect& r : rects) {
+        dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
+        batch_kernel<2><<<grid, threads, r.smem_rev, st>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss, r);
+    }
     batch_grad_reduce_kernel<<<dim3(bd.nops, unsigned(n_sets), 1), 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops, ss);
 }
 

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <vector>
 
 #include "plan.hpp"
 
@@ -39,12 +40,19 @@ struct SetStrides {
     int64_t grad;  // per-excitation gradients
 };
 
+// a rectangle of the (alpha panel) x (beta panel) grid handled by one launch
+struct TileRect {
+    int pa_lo, pa_cnt, pb_lo, pb_cnt;
+    size_t smem_fwd, smem_rev;
+};
+
 cudaError_t batch_kernels_configure();
 size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv);
-void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem, int threads,
-                          int n_sets, SetStrides ss, cudaStream_t st);
-void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot, size_t smem,
-                          int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st);
+void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
+                          int threads, int n_sets, SetStrides ss, cudaStream_t st);
+void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot,
+                          const std::vector<TileRect>& rects, int threads, double* partials, double* grad_ops, int n_sets,
+                          SetStrides ss, cudaStream_t st);
 void launch_permute(const double* in, double* out, int64_t na, int64_t nb, const uint32_t* map_a, const uint32_t* map_b,
                     cudaStream_t st);
 

@@ -347,7 +347,11 @@ void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool si
     side->panels.clear();
     side->max_panel = 0;
     side->max_classes = 0;
-    for (int e = 0; e <= m; ++e) {
+    // panels of the largest classes first: tiles of similar size are then contiguous rectangles of the panel grid
+    std::vector<int> e_order;
+    for (int e = 0; e <= m; ++e) e_order.push_back(e);
+    std::stable_sort(e_order.begin(), e_order.end(), [&](int x, int y) { return binom[m][x] > binom[m][y]; });
+    for (int e : e_order) {
         std::vector<int> ids;
         for (size_t c = 0; c < members.size(); ++c)
             if (cls_e[c] == e) ids.push_back(int(c));

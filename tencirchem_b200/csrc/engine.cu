@@ -886,10 +886,7 @@ int tcc_energy_and_grad_batch(tcc_plan* p, int n_sets, const double* params_host
     int cap = int(std::max(1.0, std::min(double(std::min(n_sets, 8192)), budget / per_set)));
     SetsWorkspace& w = g_sets_ws[p];
     if (w.cap < cap) {
-        tcc_plan* key = p;
-        SetsWorkspace old = w;
-        (void)old;
-        free_sets_ws(key);
+        free_sets_ws(p);
         SetsWorkspace& nw = g_sets_ws[p];
         const size_t vec = size_t(hp.N) * cap;
         if (cudaMalloc(&nw.ket, vec * 8) != cudaSuccess || cudaMalloc(&nw.bra, vec * 8) != cudaSuccess ||

@@ -197,7 +197,7 @@ void HostPlan::expand_tables(const OpDesc& op, uint64_t* perm, int8_t* phase, in
     const HopTable* hb = op.hop_b >= 0 ? &hops[op.hop_b] : nullptr;
     int64_t la = ha ? int64_t(ha->src.size()) : na;
     int64_t lb = hb ? int64_t(hb->src.size()) : nb;
-    auto to_ref = [&](int64_t x) { return hcb && na == 1 && false ? x : int64_t(int2ref[x]); };
+    auto to_ref = [&](int64_t x) { return int64_t(int2ref[x]); };
     for (int64_t i = 0; i < la; ++i) {
         int64_t a = ha ? to_ref(ha->src[i]) : i;
         int64_t a2 = ha ? to_ref(ha->dst[i] & 0x7fffffffu) : i;

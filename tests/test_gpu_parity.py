@@ -364,6 +364,31 @@ def test_batched_parameter_sets_chunking(monkeypatch):
         assert abs(e_b[i] - e1) < 1e-12 and np.abs(g_b[i] - g1).max() < 1e-12
 
 
+@pytest.mark.parametrize("kind,no,nv", [("uccsd", 1, 4), ("uccsd", 4, 1), ("uccsd", 1, 2), ("kupccgsd", 1, 3), ("puccd", 1, 4), ("puccd", 4, 1)])
+def test_ragged_active_spaces(kind, no, nv):
+    """Very unequal occupied / virtual counts (single electron pair, single virtual orbital)."""
+    ucc, int1e, int2e = _build(kind, no, nv)
+    params = _params(ucc.n_params)
+    h = O.get_h_from_integral(int1e, int2e, ucc.n_elec, ucc.hcb)
+    e_ref, g_ref = O.get_energy_and_grad(params, h, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb)
+    e, g = ucc.energy_and_grad(params)
+    assert abs(e - e_ref) < E_TOL and np.abs(g - g_ref).max() < G_TOL
+    c_ref = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb)
+    assert np.abs(ucc.civector(params) - c_ref).max() < C_TOL
+    O.clear_cache()
+
+
+def test_trivial_spaces():
+    """No electrons / no virtual orbitals: a one-determinant CI space and an empty excitation list."""
+    int1e, int2e = random_integral(3)
+    for n_elec in (0, 6):
+        ucc = UCC.from_integral(int1e, int2e, n_elec, ex_ops=[], param_ids=[])
+        assert ucc.civector_size == 1
+        np.testing.assert_array_equal(ucc.civector(np.zeros(0)), [1.0])
+        h = O.get_h_fcifunc_from_integral(int1e, int2e, n_elec)
+        assert abs(ucc.energy(np.zeros(0)) - h(np.ones(1))[0]) < 1e-12
+
+
 def test_device_resident_api():
     import torch
 

@@ -229,31 +229,26 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
             }
         };
         fetch(0, cur0, cur1);
-        int cnt_n = bd.nops > 0 ? sops[0].cnt : 0;
-        int off_n = bd.nops > 0 ? sops[0].off : 0;
-        double cs_n = bd.nops > 0 ? sops[0].cs : 0.0, sn_n = bd.nops > 0 ? sops[0].sn : 0.0;
         for (int tb = 0; tb < bd.nops; tb += BK_DEPTH) {
             fetch(tb + BK_DEPTH, nxt0, nxt1);
 #pragma unroll
             for (int j = 0; j < BK_DEPTH; ++j) {
                 const int t = tb + j;
+                accs[j] = 0.0;
                 if (t < bd.nops) {
-                    const int cnt = cnt_n, off = off_n;
-                    const double cs = cs_n, sn = sn_n;
-                    if (t + 1 < bd.nops) {  // next record read before this excitation's barrier
-                        cnt_n = sops[t + 1].cnt;
-                        off_n = sops[t + 1].off;
-                        cs_n = sops[t + 1].cs;
-                        sn_n = sops[t + 1].sn;
+                    const int cnt = sops[t].cnt;
+                    if (tid < cnt) {  // warps without a pair for this excitation go straight to the barrier
+                        const double cs = sops[t].cs, sn = sops[t].sn;
+                        double acc = 0.0;
+                        rotate_one(cur0[j], cs, sn, acc);
+                        if (tid + nthreads < cnt) {
+                            rotate_one(cur1[j], cs, sn, acc);
+                            const int off = sops[t].off;
+                            for (int idx = tid + 2 * nthreads; idx < cnt; idx += nthreads) rotate_one(__ldg(plist + off + idx), cs, sn, acc);
+                        }
+                        accs[j] = acc;
                     }
-                    double acc = 0.0;
-                    if (tid < cnt) rotate_one(cur0[j], cs, sn, acc);
-                    if (tid + nthreads < cnt) rotate_one(cur1[j], cs, sn, acc);
-                    for (int idx = tid + 2 * nthreads; idx < cnt; idx += nthreads) rotate_one(__ldg(plist + off + idx), cs, sn, acc);
-                    accs[j] = acc;
                     __syncthreads();
-                } else {
-                    accs[j] = 0.0;
                 }
             }
             if (NV == 2) {

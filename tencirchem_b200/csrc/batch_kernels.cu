@@ -198,6 +198,9 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
         const uint32_t* __restrict__ plist = bd.plist;
         uint32_t cur0[BK_DEPTH], cur1[BK_DEPTH], nxt0[BK_DEPTH], nxt1[BK_DEPTH];
         double accs[BK_DEPTH];
+        const uint32_t* __restrict__ lp0 = plist + tid;
+        const uint32_t* __restrict__ lp1 = lp0 + nthreads;
+        const int warp_first = warp << 5;
         auto fetch = [&](int tbase, uint32_t* e0, uint32_t* e1) {
 #pragma unroll
             for (int j = 0; j < BK_DEPTH; ++j) {
@@ -205,9 +208,12 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
                 e0[j] = 0;
                 e1[j] = 0;
                 if (t < bd.nops) {
-                    const int off = sops[t].off, cnt = sops[t].cnt;
-                    if (tid < cnt) e0[j] = __ldg(plist + off + tid);
-                    if (tid + nthreads < cnt) e1[j] = __ldg(plist + off + tid + nthreads);
+                    const int cnt = sops[t].cnt;
+                    if (warp_first < cnt) {  // warp-uniform: warps without pairs skip the address arithmetic too
+                        const int off = sops[t].off;
+                        if (tid < cnt) e0[j] = __ldg(lp0 + off);
+                        if (tid + nthreads < cnt) e1[j] = __ldg(lp1 + off);
+                    }
                 }
             }
         };

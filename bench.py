@@ -33,8 +33,9 @@ WORKLOADS = {"16o": 16, "14o": 14, "12o": 12, "10o": 10, "8o": 8, "4o": 4}
 METRIC = "uccsd_energy_and_grad_evals_per_s"
 
 
-def workload_desc(n):
-    return f"UCCSD energy_and_grad ({n}e,{n}o), random_integral seed 2077, unscreened generator order"
+def workload_desc(n, ansatz="uccsd"):
+    names = {"uccsd": "UCCSD (unscreened, generator order)", "kupccgsd": "kUpCCGSD (k=3)", "puccd": "pUCCD (hard-core bosons)"}
+    return f"{names[ansatz]} energy_and_grad ({n}e,{n}o), random_integral seed 2077"
 
 
 # ----------------------------------------------------------------------------------------------
@@ -99,7 +100,7 @@ def measured_peak_hbm():
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_sample(n, n_ops_sample=2):
+def cpu_reference_sample(n, n_ops_sample=2, ansatz="uccsd"):
     """Times the oracle port of the reference numpy engine (nocache / 'civector-large' form, which is what
     the reference selects above 16 qubits, ucc.py:233-239) on a bounded sample and extrapolates to one
     energy_and_grad evaluation by operation counts."""
@@ -107,11 +108,12 @@ def cpu_reference_sample(n, n_ops_sample=2):
     from oracle import pools
 
     no = n // 2
-    ops, pids = pools.uccsd_ex_ops(no, n - no)
+    hcb = ansatz == "puccd"
+    ops, pids = {"uccsd": pools.uccsd_ex_ops, "kupccgsd": pools.kupccgsd_ex_ops, "puccd": pools.puccd_ex_ops}[ansatz](no, n - no)
     m = len(ops)
-    nq = 2 * n
+    nq = n if hcb else 2 * n
     t0 = time.perf_counter()
-    ci_strings, strs2addr = O.get_ci_strings(nq, n, False, strs2addr=True)
+    ci_strings, strs2addr = O.get_ci_strings(nq, n, hcb, strs2addr=True)
     t_strings = time.perf_counter() - t0
     size = len(ci_strings)
     rng = np.random.default_rng(0)
@@ -123,7 +125,7 @@ def cpu_reference_sample(n, n_ops_sample=2):
     t_tab = t_fwd = t_rev = 0.0
     for f_idx in picks:
         t0 = time.perf_counter()
-        perm, phase, f2 = O.get_operators(nq, n, strs2addr, tuple(f_idx), ci_strings, False)
+        perm, phase, f2 = O.get_operators(nq, n, strs2addr, tuple(f_idx), ci_strings, hcb)
         t1 = time.perf_counter()
         ket = O.evolve_excitation(ket, perm, phase, f2, 1 - np.cos(0.3), np.sin(0.3))
         t2 = time.perf_counter()
@@ -139,16 +141,23 @@ def cpu_reference_sample(n, n_ops_sample=2):
     t_tab, t_fwd, t_rev = t_tab / k, t_fwd / k, t_rev / k
     del ket, bra, ci_strings
     # H.c: the oracle's Knowles-Handy port at a size that fits, scaled by the 2 n^4 N flop count
-    ns = min(n, 10)
-    i1, i2 = O.random_integral(ns)
-    h = O.get_h_fcifunc_from_integral(i1, i2, ns)
     from math import comb
-    x = rng.standard_normal(comb(ns, ns // 2) ** 2)
+    if hcb:
+        ns = n
+        i1, i2 = O.random_integral(ns)
+        h = O.get_h_fcifunc_hcb_from_integral(i1, i2, ns)
+        x = rng.standard_normal(comb(ns, ns // 2))
+        scale = 1.0
+    else:
+        ns = min(n, 10)
+        i1, i2 = O.random_integral(ns)
+        h = O.get_h_fcifunc_from_integral(i1, i2, ns)
+        x = rng.standard_normal(comb(ns, ns // 2) ** 2)
+        scale = (n**4 * comb(n, n // 2) ** 2) / (ns**4 * comb(ns, ns // 2) ** 2)
     h(x)
     t0 = time.perf_counter()
     h(x)
     t_sig_small = time.perf_counter() - t0
-    scale = (n**4 * comb(n, n // 2) ** 2) / (ns**4 * comb(ns, ns // 2) ** 2)
     t_sigma = t_sig_small * scale
     # civector-large rebuilds the tables in both sweeps (evolve_civector.py:253-308); up to 16 qubits the
     # reference defaults to the cached-table engine (ucc.py:233-239) and the build is staging, not per call
@@ -171,7 +180,7 @@ def run_reference(args):
     times = []
     for step in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        res = cpu_reference_sample(n, n_ops_sample=1 if step < args.warmup else 2)
+        res = cpu_reference_sample(n, n_ops_sample=1 if step < args.warmup else 2, ansatz=args.ansatz)
         if step >= args.warmup:
             times.append(1.0 / res["value"])
     t_eval = float(np.mean(times))
@@ -179,7 +188,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": 1.0 / t_eval, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_eval, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(n), "note": "CPU oracle port of the reference numpy engine; each step is a bounded sample extrapolated by operation counts"},
+        "config": {"workload": workload_desc(n, args.ansatz), "note": "CPU oracle port of the reference numpy engine; each step is a bounded sample extrapolated by operation counts"},
         "cpu_baseline": {**res, "value": 1.0 / t_eval},
         "e2e": {"value": 1.0 / t_eval, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -192,7 +201,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from tencirchem_b200 import UCCSD
+    from tencirchem_b200 import KUPCCGSD, PUCCD, UCCSD
     from tencirchem_b200.evolve_civector import _bind_hamiltonian, get_plan
     from tencirchem_b200.hamiltonian import random_integral
 
@@ -208,12 +217,13 @@ def run_b200(args):
 
     n = WORKLOADS[args.workload]
     int1e, int2e = random_integral(n)
-    ucc = UCCSD.from_integral(int1e, int2e, n)
+    np.random.seed(2077)  # kUpCCGSD draws its initial guess from the global stream
+    ucc = {"uccsd": UCCSD, "kupccgsd": KUPCCGSD, "puccd": PUCCD}[args.ansatz].from_integral(int1e, int2e, n)
     m, p_count = len(ucc.ex_ops), ucc.n_params
     size = ucc.civector_size
 
     t0 = time.perf_counter()
-    plan = get_plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False, device=local_rank)
+    plan = get_plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb, device=local_rank)
     _bind_hamiltonian(plan, ucc.hamiltonian)
     staging_s = time.perf_counter() - t0
 
@@ -295,7 +305,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(n), "n_determinants": size, "n_excitations": m, "n_params": p_count,
+        "config": {"workload": workload_desc(n, args.ansatz), "n_determinants": size, "n_excitations": m, "n_params": p_count,
                    "l2": "inputs larger than L2 (1.3 GB vectors vs 126 MB)" if size * 8 > 2.5e8 else "vectors fit in L2; no flush",
                    "multi_gpu": "independent theta sets per rank, no data-path collective" if world > 1 else "single GPU",
                    "n_batches": plan.n_batches, "staging_s": round(staging_s, 2)},
@@ -313,7 +323,7 @@ def run_b200(args):
     }
     if not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_reference_sample(n, n_ops_sample=2)
+            line["cpu_baseline"] = cpu_reference_sample(n, n_ops_sample=2, ansatz=args.ansatz)
         except Exception as exc:  # pragma: no cover
             line["cpu_baseline"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
@@ -368,7 +378,7 @@ def run_b200_batched(args, plan, ucc, theta, barrier, world, rank, n, staging_s)
         "metric": METRIC, "value": evals / (dev_ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(n) + f", {bsz} random theta per step (batched)", "n_determinants": size,
+        "config": {"workload": workload_desc(n, args.ansatz) + f", {bsz} random theta per step (batched)", "n_determinants": size,
                    "n_excitations": m, "n_params": p_count, "n_batches": plan.n_batches, "staging_s": round(staging_s, 2),
                    "l2": "vectors of all sets of a step: %.1f MB" % (4 * 8 * size * bsz / 1e6)},
         "e2e": {"value": evals / (wall_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": 8 * p_count * bsz,
@@ -382,7 +392,7 @@ def run_b200_batched(args, plan, ucc, theta, barrier, world, rank, n, staging_s)
     }
     if not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_reference_sample(n, n_ops_sample=2)
+            line["cpu_baseline"] = cpu_reference_sample(n, n_ops_sample=2, ansatz=args.ansatz)
         except Exception as exc:  # pragma: no cover
             line["cpu_baseline"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
@@ -397,6 +407,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="16o", choices=sorted(WORKLOADS))
+    ap.add_argument("--ansatz", default="uccsd", choices=["uccsd", "kupccgsd", "puccd"],
+                    help="ansatz of the workload (default: unscreened UCCSD, the configuration the metric is quoted on)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0,
                     help="batched-theta mode: each step evaluates this many parameter sets in the same launches (small active spaces)")

@@ -300,6 +300,11 @@ def run_b200(args):
     phases = {s: {"ms_per_step": round(v[0] / args.steps, 3), "launches_per_step": v[1] // args.steps,
                   "algorithmic_GBps": round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 else None,
                   "share": round(v[0] / total_prof_ms, 4) if total_prof_ms else None} for s, v in prof.items()}
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {}).get(dom)
+    except Exception:
+        pass
     dense_bytes = (48 * m + 16) * size
     line = {
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -313,7 +318,8 @@ def run_b200(args):
                 "note": "public API UCCSD.energy_and_grad(params): host params in, host (energy, gradient) out; the CI vectors never leave HBM"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kernel_names.get(dom, dom), "phase": dom, "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                     "traffic_source": "ncu --set full capture of this kernel, bytes per launch (profiles/ncu_traffic.json)" if traffic else None,
                      "avg_launch_us": 1e3 * d_ms / max(d_launch, 1), "launches": d_launch,
                      "algorithmic_bytes_per_launch": d_bytes / max(d_launch, 1)},
         "effective_dense_model_GBps": dense_bytes / (dev_ms / args.steps * 1e-3) / 1e9,

@@ -185,6 +185,23 @@ class UCC:
         )
         return float(e + self.e_core), np.asarray(g)
 
+    def energy_and_grad_batch(self, params_batch, engine: str = None):
+        """Additive API (gap i): many parameter vectors ``[n_sets, n_params]`` in the same
+        kernel launches; returns ``(energies [n_sets], grads [n_sets, n_params])``.  Starts from the HF determinant."""
+        from .evolve_civector import _bind_hamiltonian, get_plan
+
+        self._sanity_check()
+        self._check_engine(engine)
+        if self.init_state is not None:
+            raise ValueError("energy_and_grad_batch starts from the HF determinant; init_state is not supported")
+        params_batch = np.asarray(params_batch, dtype=np.float64)
+        if params_batch.ndim != 2 or params_batch.shape[1] != self.n_params:
+            raise ValueError(f"Incompatible parameter shape. (n_sets, {self.n_params}) is desired. Got {params_batch.shape}")
+        plan = get_plan(self.n_qubits, self.n_elec, self.ex_ops, self.param_ids, self.hcb)
+        _bind_hamiltonian(plan, self.hamiltonian)
+        e, g = plan.energy_and_grad_batch(params_batch)
+        return e + self.e_core, g
+
     def apply_excitation(self, state, ex_op: Tuple, engine: str = None):
         """ucc.py:709-737."""
         self._check_engine(engine)

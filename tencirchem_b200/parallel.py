@@ -62,10 +62,8 @@ def energy_and_grad_batch(plan, thetas: np.ndarray, rank: int = 0, world: int = 
     call): each rank evaluates its slice on its own GPU with the device-resident path; results are gathered."""
     thetas = np.asarray(thetas, dtype=np.float64)
     mine = shard_parameter_sets(thetas, rank, world)
-    energies = np.zeros(len(mine))
-    grads = np.zeros((len(mine), plan.n_params))
-    for i, th in enumerate(mine):
-        energies[i], grads[i] = plan.energy_and_grad_dev(th)
+    # all sets of the rank's slice share every kernel launch (tcc_energy_and_grad_batch)
+    energies, grads = plan.energy_and_grad_batch(mine) if len(mine) else (np.zeros(0), np.zeros((0, plan.n_params)))
     if world == 1:
         return energies, grads
     return gather_results(energies, grads, len(thetas), rank, world)

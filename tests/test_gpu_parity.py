@@ -350,6 +350,27 @@ def test_batched_parameter_sets(kind, no, nv):
         plan.energy_and_grad_batch(np.zeros((3, max(ucc.n_params - 1, 0))))
 
 
+def test_batched_parameter_sets_through_the_ansatz_class_and_rank_sharding():
+    from tencirchem_b200.parallel import energy_and_grad_batch, shard_bounds
+
+    ucc, int1e, int2e = _build("kupccgsd", 2, 2)
+    rng = np.random.default_rng(3)
+    thetas = rng.random((9, ucc.n_params)) - 0.5
+    e, g = ucc.energy_and_grad_batch(thetas)
+    for i in (0, 8):
+        e1, g1 = ucc.energy_and_grad(thetas[i])
+        assert abs(e[i] - e1) < 1e-12 and np.abs(g[i] - g1).max() < 1e-12
+    with pytest.raises(ValueError, match="Incompatible parameter shape"):
+        ucc.energy_and_grad_batch(thetas[:, :-1])
+    # the per-rank slice of a 2-rank job evaluates exactly its rows (world == 1 path of each rank)
+    plan = Plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids)
+    plan.set_hamiltonian(int1e, int2e)
+    lo, hi = shard_bounds(len(thetas), 1, 2)
+    e_r, g_r = energy_and_grad_batch(plan, thetas[lo:hi])
+    np.testing.assert_allclose(e_r, e[lo:hi], atol=1e-12)
+    np.testing.assert_allclose(g_r, g[lo:hi], atol=1e-12)
+
+
 def test_batched_parameter_sets_chunking(monkeypatch):
     """More sets than fit the memory budget at once are processed in chunks."""
     monkeypatch.setenv("TCC_B200_BATCH_MEM_MB", "1")

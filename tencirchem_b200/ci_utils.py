@@ -1,7 +1,8 @@
-"""Host-side CI-string helpers with the reference's names and results
-(tencirchem/static/ci_utils.py:16-87), bit-exact.  PySCF's ``cistring.make_strings`` is replaced by
-the plan's own enumeration (ascending integers of fixed popcount, include/tcc_b200.h
-``tcc_ci_strings_spin``); the ``[N]``-long arrays are only materialised when a caller asks for them.
+"""Host-side CI-string helpers: same names, arguments and results as tencirchem/static/ci_utils.py:16-87
+(bit-exact), built on the engine's own string enumeration instead of PySCF's ``cistring`` module.
+
+The ``[N]``-long arrays are only materialised when a caller asks for them: the engine itself never needs them
+(everything factorises per spin string).
 """
 from __future__ import annotations
 
@@ -12,69 +13,71 @@ import numpy as np
 from .plan import Plan
 
 UINT = np.uint64
+_MAX_TABLE_BITS = 32
 
 
-def _spin_strings(n_qubits, n_elec, hcb):
-    return Plan(n_qubits, n_elec, (), (), hcb=hcb, device=None).ci_strings_spin()
+def _reference_order_strings(n_qubits: int, n_elec: int, hcb: bool) -> np.ndarray:
+    """Occupation strings of one spin (all orbitals for hcb) in the reference's address order, from
+    ``tcc_ci_strings_spin`` (ascending integers with n_elec/2 bits set)."""
+    host_plan = Plan(n_qubits, n_elec, (), (), hcb=hcb, device=None)
+    return host_plan.ci_strings_spin()
 
 
 def get_ci_strings(n_qubits, n_elec, hcb, strs2addr=False):
-    """ci_utils.py:16-37."""
-    if 2**n_qubits > np.iinfo(UINT).max:
+    """ci_utils.py:16-37: determinant bit strings (alpha string in the high half, alpha-major) and, on request,
+    the string -> address lookup table (zero for strings outside the space)."""
+    if (1 << n_qubits) > np.iinfo(UINT).max:
         raise ValueError(f"Too many qubits: {n_qubits}, try using complex128 datatype")
-    spin = _spin_strings(n_qubits, n_elec, hcb)
-    if not hcb:
-        half = n_qubits // 2
-        ci_strings = ((spin << UINT(half)).reshape(-1, 1) + spin.reshape(1, -1)).ravel()
-        table_bits = half
+    one_spin = _reference_order_strings(n_qubits, n_elec, hcb)
+    if hcb:
+        bits_in_table, determinants = n_qubits, one_spin
     else:
-        ci_strings = spin
-        table_bits = n_qubits
-    if strs2addr:
-        if table_bits > 32:
-            raise ValueError(f"Too many qubits: {n_qubits} for a dense string lookup table")
-        table = np.zeros(2**table_bits, dtype=UINT)
-        table[spin] = np.arange(len(spin), dtype=UINT)
-        return ci_strings, table
-    return ci_strings
+        bits_in_table = n_qubits // 2
+        high = one_spin << UINT(bits_in_table)
+        determinants = np.add.outer(high, one_spin).reshape(-1)
+    if not strs2addr:
+        return determinants
+    if bits_in_table > _MAX_TABLE_BITS:
+        raise ValueError(f"Too many qubits: {n_qubits} for a dense string lookup table")
+    lookup = np.zeros(1 << bits_in_table, dtype=UINT)
+    lookup[one_spin] = np.arange(one_spin.size, dtype=UINT)
+    return determinants, lookup
 
 
 def get_addr(excitation, n_qubits, n_elec, strs2addr, hcb, num_strings=None):
-    """ci_utils.py:40-49."""
-    excitation = np.asarray(excitation, dtype=UINT)
+    """ci_utils.py:40-49: address of each bit string; strings outside the space map to 0, like upstream."""
+    strings = np.asarray(excitation, dtype=UINT)
     if hcb:
-        return strs2addr[excitation]
+        return strs2addr[strings]
     half = n_qubits // 2
-    alpha = excitation >> UINT(half)
-    beta = excitation & UINT(2**half - 1)
-    if num_strings is None:
-        num_strings = comb(half, n_elec // 2)
-    return strs2addr[alpha] * UINT(num_strings) + strs2addr[beta]
+    n_per_spin = comb(half, n_elec // 2) if num_strings is None else num_strings
+    row = strs2addr[strings >> UINT(half)]
+    col = strs2addr[strings & UINT((1 << half) - 1)]
+    return row * UINT(n_per_spin) + col
 
 
 def get_ex_bitstring(n_qubits, n_elec, ex_op, hcb):
-    """ci_utils.py:52-71."""
-    if not hcb:
-        bits = (["0"] * (n_qubits // 2 - n_elec // 2) + ["1"] * (n_elec // 2)) * 2
-    else:
-        bits = ["0"] * (n_qubits - n_elec // 2) + ["1"] * (n_elec // 2)
-    bits = bits[::-1]
-    assert len(ex_op) in (2, 4)
-    half = len(ex_op) // 2
-    for i in ex_op[half:]:
-        bits[i] = "0"
-    for i in ex_op[:half]:
-        bits[i] = "1"
-    return "".join(reversed(bits))
+    """ci_utils.py:52-71: the HF determinant with the excitation applied, as a bit string (qubit 0 rightmost)."""
+    if len(ex_op) not in (2, 4):
+        raise AssertionError("excitation tuples have 2 or 4 indices")
+    n_occ = n_elec // 2
+    hf = (1 << n_occ) - 1
+    det = hf if hcb else hf | (hf << (n_qubits // 2))
+    n_create = len(ex_op) // 2
+    for q in ex_op[n_create:]:
+        det &= ~(1 << q)
+    for q in ex_op[:n_create]:
+        det |= 1 << q
+    return format(det, f"0{n_qubits}b")
 
 
 def civector_to_statevector(civector, n_qubits, ci_strings):
-    """ci_utils.py:74-76.  Raises instead of allocating 2**n_qubits doubles beyond 32 qubits."""
-    if n_qubits > 32:
+    """ci_utils.py:74-76.  Raises instead of allocating 2**n_qubits doubles beyond 32 qubits (SURVEY.md 8b-ii)."""
+    if n_qubits > _MAX_TABLE_BITS:
         raise ValueError(f"statevector of {n_qubits} qubits is too large to materialise; use the CI vector")
-    sv = np.zeros(2**n_qubits, dtype=np.float64)
-    sv[np.asarray(ci_strings)] = np.asarray(civector, dtype=np.float64)
-    return sv
+    full = np.zeros(1 << n_qubits, dtype=np.float64)
+    full[np.asarray(ci_strings)] = np.asarray(civector, dtype=np.float64)
+    return full
 
 
 def statevector_to_civector(statevector, ci_strings):
@@ -83,7 +86,7 @@ def statevector_to_civector(statevector, ci_strings):
 
 
 def get_init_civector(len_ci):
-    """ci_utils.py:83-87 (host copy; the engine creates it on the device)."""
-    c = np.zeros(len_ci, dtype=np.float64)
-    c[0] = 1.0
-    return c
+    """ci_utils.py:83-87 (host copy; the engine creates the HF vector on the device)."""
+    hf = np.zeros(len_ci, dtype=np.float64)
+    hf[0] = 1.0
+    return hf

@@ -2,6 +2,7 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -537,6 +538,9 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
         }
     };
     std::vector<Ent> ea_list, eb_list;
+    std::vector<uint32_t> raw;
+    std::vector<char> taken;
+    const bool bank_order = std::getenv("TCC_B200_BANK_ORDER") ? std::atoi(std::getenv("TCC_B200_BANK_ORDER")) != 0 : true;
     for (size_t t = 0; t < out->ops.size(); ++t) {
         const BatchOp& bo = out->ops[t];
         for (int ea = 0; ea <= ma; ++ea) {
@@ -549,9 +553,41 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
                 const size_t slot = ((t * (ma + 1) + ea) * (mb + 1) + eb) * 2;
                 out->plist_index[slot] = int32_t(out->plist.size());
                 out->plist_index[slot + 1] = int32_t(ea_list.size() * eb_list.size());
+                raw.clear();
                 for (const Ent& a : ea_list)
                     for (const Ent& b : eb_list)
-                        out->plist.push_back((a.s * ld + b.s) | ((a.d * ld + b.d) << 15) | ((a.sg ^ b.sg) << 30));
+                        raw.push_back((a.s * ld + b.s) | ((a.d * ld + b.d) << 15) | ((a.sg ^ b.sg) << 30));
+                if (bank_order && raw.size() > 16) {
+                    // The pairs of one excitation are independent, so their order is free: emit them in groups of
+                    // 16 consecutive entries (one shared-memory wavefront of a 64-bit access) whose first elements
+                    // fall into different 8-byte banks, and likewise the second elements, as far as a greedy
+                    // search in a small window finds them.
+                    taken.assign(raw.size(), 0);
+                    size_t head = 0, emitted = 0;
+                    while (emitted < raw.size()) {
+                        uint32_t m1 = 0, m2 = 0;
+                        for (int kk = 0; kk < 16 && emitted < raw.size(); ++kk) {
+                            while (head < raw.size() && taken[head]) ++head;
+                            size_t pick = head;
+                            const size_t lim = std::min(raw.size(), head + 96);
+                            for (size_t c = head; c < lim; ++c) {
+                                if (taken[c]) continue;
+                                const uint32_t b1 = 1u << (raw[c] & 15u), b2 = 1u << ((raw[c] >> 15) & 15u);
+                                if (!(m1 & b1) && !(m2 & b2)) {
+                                    pick = c;
+                                    break;
+                                }
+                            }
+                            taken[pick] = 1;
+                            m1 |= 1u << (raw[pick] & 15u);
+                            m2 |= 1u << ((raw[pick] >> 15) & 15u);
+                            out->plist.push_back(raw[pick]);
+                            ++emitted;
+                        }
+                    }
+                } else {
+                    out->plist.insert(out->plist.end(), raw.begin(), raw.end());
+                }
             }
         }
     }

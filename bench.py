@@ -29,7 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {"18o": 18, "16o": 16, "14o": 14, "12o": 12, "10o": 10, "8o": 8, "4o": 4}
+WORKLOADS = {"18o": 18, "16o": 16, "14o": 14, "12o": 12, "10o": 10, "8o": 8, "6o": 6, "4o": 4, "2o": 2}
 METRIC = "uccsd_energy_and_grad_evals_per_s"
 
 

@@ -33,9 +33,10 @@ WORKLOADS = {"18o": 18, "16o": 16, "14o": 14, "12o": 12, "10o": 10, "8o": 8, "6o
 METRIC = "uccsd_energy_and_grad_evals_per_s"
 
 
-def workload_desc(n, ansatz="uccsd"):
+def workload_desc(n, ansatz="uccsd", integrals="random"):
     names = {"uccsd": "UCCSD (unscreened, generator order)", "kupccgsd": "kUpCCGSD (k=3)", "puccd": "pUCCD (hard-core bosons)"}
-    return f"{names[ansatz]} energy_and_grad ({n}e,{n}o), random_integral seed 2077"
+    src = "random_integral seed 2077" if integrals == "random" else f"H{n} chain STO-3G 0.8 A (RHF MO integrals)"
+    return f"{names[ansatz]} energy_and_grad ({n}e,{n}o), {src}"
 
 
 # ----------------------------------------------------------------------------------------------
@@ -190,7 +191,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": 1.0 / t_eval, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_eval, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(n, args.ansatz), "note": "CPU oracle port of the reference numpy engine; each step is a bounded sample extrapolated by operation counts"},
+        "config": {"workload": workload_desc(n, args.ansatz, args.integrals), "note": "CPU oracle port of the reference numpy engine; each step is a bounded sample extrapolated by operation counts"},
         "cpu_baseline": {**res, "value": 1.0 / t_eval},
         "e2e": {"value": 1.0 / t_eval, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -218,7 +219,12 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = WORKLOADS[args.workload]
-    int1e, int2e = random_integral(n)
+    if args.integrals == "hchain":
+        from tencirchem_b200.hchain import h_chain_integrals
+
+        int1e, int2e, _, _ = h_chain_integrals(n)
+    else:
+        int1e, int2e = random_integral(n)
     np.random.seed(2077)  # kUpCCGSD draws its initial guess from the global stream
     ucc = {"uccsd": UCCSD, "kupccgsd": KUPCCGSD, "puccd": PUCCD}[args.ansatz].from_integral(int1e, int2e, n)
     m, p_count = len(ucc.ex_ops), ucc.n_params
@@ -312,7 +318,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(n, args.ansatz), "n_determinants": size, "n_excitations": m, "n_params": p_count,
+        "config": {"workload": workload_desc(n, args.ansatz, args.integrals), "n_determinants": size, "n_excitations": m, "n_params": p_count,
                    "l2": "inputs larger than L2 (1.3 GB vectors vs 126 MB)" if size * 8 > 2.5e8 else "vectors fit in L2; no flush",
                    "multi_gpu": "independent theta sets per rank, no data-path collective" if world > 1 else "single GPU",
                    "n_batches": plan.n_batches, "staging_s": round(staging_s, 2)},
@@ -386,7 +392,7 @@ def run_b200_batched(args, plan, ucc, theta, barrier, world, rank, n, staging_s)
         "metric": METRIC, "value": evals / (dev_ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(n, args.ansatz) + f", {bsz} random theta per step (batched)", "n_determinants": size,
+        "config": {"workload": workload_desc(n, args.ansatz, args.integrals) + f", {bsz} random theta per step (batched)", "n_determinants": size,
                    "n_excitations": m, "n_params": p_count, "n_batches": plan.n_batches, "staging_s": round(staging_s, 2),
                    "l2": "vectors of all sets of a step: %.1f MB" % (4 * 8 * size * bsz / 1e6)},
         "e2e": {"value": evals / (wall_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": 8 * p_count * bsz,
@@ -417,6 +423,9 @@ def main():
     ap.add_argument("--workload", default="16o", choices=sorted(WORKLOADS))
     ap.add_argument("--ansatz", default="uccsd", choices=["uccsd", "kupccgsd", "puccd"],
                     help="ansatz of the workload (default: unscreened UCCSD, the configuration the metric is quoted on)")
+    ap.add_argument("--integrals", default="random", choices=["random", "hchain"],
+                    help="random_integral(n, seed 2077) used as MO integrals (default, SURVEY.md 8d) or the literal linear H_n chain, "
+                         "STO-3G, 0.8 A, RHF orbitals (tencirchem_b200/hchain.py; the H4/H8/H12 molecules of BASELINE.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0,
                     help="batched-theta mode: each step evaluates this many parameter sets in the same launches (small active spaces)")

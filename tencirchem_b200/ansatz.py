@@ -207,6 +207,11 @@ class UCC:
         self._check_engine(engine)
         return engine_ucc.apply_excitation(state, self.n_qubits, self.n_elec, ex_op, hcb=self.hcb)
 
+    @property
+    def e_ucc(self) -> float:
+        """ucc.py:1033-1038."""
+        return self.energy()
+
     def kernel(self) -> float:
         """ucc.py:337-378: L-BFGS-B over ``energy_and_grad``."""
         from scipy.optimize import minimize

@@ -460,6 +460,62 @@ def test_properties_full_size_16o(monkeypatch):
     torch.cuda.empty_cache()
 
 
+def test_h_chain_published_energies_on_the_engine():
+    """Literal BASELINE molecules (PySCF-free STO-3G integrals, tencirchem_b200/hchain.py) through the engine against
+    the numbers the reference publishes: H8 (2e,2o) active space (ucc_functions.ipynb cells 31-42)."""
+    from tencirchem_b200.hchain import active_space_integrals, h_chain_integrals
+
+    k = KAT["h_chain_sto3g"]
+    int1e, int2e, e_nuc, e_hf = h_chain_integrals(8)
+    h1, h2, e_core = active_space_integrals(int1e, int2e, e_nuc, 8, (2, 2))
+    ucc = UCCSD.from_integral(h1, h2, 2, e_core)
+    assert abs(ucc.energy(np.zeros(2)) - k["h8_e_hf"]) < 1e-11
+    e, g = ucc.energy_and_grad(np.zeros(2))
+    np.testing.assert_allclose(g, k["h8_cas22_grad_at_zero"], atol=3e-7)
+    assert abs(ucc.kernel() - k["h8_cas22_uccsd"]) < 1e-7
+
+
+def test_adapt_vqe_tutorial_h4_on_the_engine():
+    """The reference's ADAPT-VQE tutorial (adapt_vqe.ipynb cells 3-11) replayed on the B200 engine for the literal H4
+    chain: pool gradients through civector / hamiltonian / apply_excitation, operator picks and the optimised
+    energy of every iteration against the published output."""
+    from collections import defaultdict
+
+    from tencirchem_b200.hchain import h_chain_integrals
+
+    k = KAT["h_chain_sto3g"]
+    int1e, int2e, e_nuc, _ = h_chain_integrals(4)
+    probe = UCCSD.from_integral(int1e, int2e, 4, e_nuc)
+    ex1_ops, ex1_ids, _ = probe.get_ex1_ops()
+    ex2_ops, ex2_ids, _ = probe.get_ex2_ops()
+    pool = defaultdict(list)
+    for op, pid in zip(ex1_ops, ex1_ids):
+        pool[(1, pid)].append(op)
+    for op, pid in zip(ex2_ops, ex2_ids):
+        pool[(2, pid)].append(op)
+    pool = list(pool.values())
+    ucc = UCC.from_integral(int1e, int2e, 4, e_nuc, ex_ops=[], param_ids=[])
+    ucc.params = []
+    for it, (pick_pub, e_pub) in enumerate(zip(k["h4_adapt_picks"], k["h4_adapt_energies"])):
+        psi = ucc.civector()
+        bra = ucc.hamiltonian(psi)
+        grads = [2 * sum(bra @ ucc.apply_excitation(psi, op) for op in ops_) for ops_ in pool]
+        if it == 0:
+            assert abs(np.linalg.norm(grads) - k["h4_adapt_iter0_norm"]) < 2e-7
+            pub = {str([list(o) for o in ops_]): g for ops_, g in k["h4_adapt_iter0"]}
+            for ops_, g in zip(pool, grads):
+                key = str([list(o) for o in ops_])
+                assert abs(g - pub.get(key, 0.0)) < 3e-7, (ops_, g)
+        chosen = pool[int(np.argmax(np.abs(grads)))]
+        assert [list(o) for o in chosen] == pick_pub, (it, chosen, pick_pub)
+        ucc.ex_ops.extend(chosen)
+        ucc.params = list(ucc.params) + [0]
+        ucc.param_ids = list(ucc.param_ids) + [len(ucc.params) - 1] * len(chosen)
+        ucc.init_guess = ucc.params
+        ucc.kernel()
+        assert abs(ucc.e_ucc - e_pub) < 2e-6, (it, ucc.e_ucc, e_pub)
+
+
 def test_device_resident_api():
     import torch
 

@@ -187,3 +187,56 @@ def test_golden_file_is_current():
     e, g = O.get_energy_and_grad(gold["uccsd_2_3_params"], h, 10, 4, ops, pids)
     assert abs(e - float(gold["uccsd_2_3_energy"])) < 1e-13
     np.testing.assert_allclose(g, gold["uccsd_2_3_grad"], atol=1e-13)
+
+
+# ---- literal hydrogen chains (BASELINE.json configs 0-2): PySCF-free STO-3G integrals + RHF ----------------------
+def test_hchain_integrals_reproduce_published_h2():
+    """tencirchem_b200/hchain.py (s-Gaussian integrals, RHF, MO transform) against the MO integrals and energies the
+    reference publishes for H2 (ucc_functions.ipynb)."""
+    from tencirchem_b200.hchain import h_chain_integrals
+
+    k = KAT["h2_sto3g"]
+    int1e, int2e, e_nuc, e_hf = h_chain_integrals(2, 0.741)
+    assert abs(e_nuc - k["e_nuc"]) < 1e-14 and abs(e_hf - k["e_hf"]) < 1e-12
+    assert abs(int1e[0, 0] - k["h00"]) < 1e-12 and abs(int1e[1, 1] - k["h11"]) < 1e-12 and abs(int1e[0, 1]) < 1e-12
+    for idx, name in [((0, 0, 0, 0), "J00"), ((1, 1, 1, 1), "J11"), ((0, 0, 1, 1), "J01"), ((0, 1, 0, 1), "K01"), ((0, 1, 1, 0), "K01")]:
+        assert abs(int2e[idx] - k[name]) < 1e-12, name
+
+
+def test_h8_active_space_published_energies():
+    from scipy.optimize import minimize
+
+    from tencirchem_b200.hchain import active_space_integrals, h_chain_integrals
+
+    k = KAT["h_chain_sto3g"]
+    int1e, int2e, e_nuc, e_hf = h_chain_integrals(8)
+    assert abs(e_hf - k["h8_e_hf"]) < 1e-11
+    h1, h2, e_core = active_space_integrals(int1e, int2e, e_nuc, 8, (2, 2))
+    ops, pids = pools.uccsd_ex_ops(1, 1)
+    h = O.get_h_fcifunc_from_integral(h1, h2, 2)
+    e0, g0 = O.get_energy_and_grad(np.zeros(2), h, 4, 2, ops, pids)
+    assert abs(e0 + e_core - k["h8_e_hf"]) < 1e-11  # ucc.energy(zeros) == e_hf, cell 37
+    np.testing.assert_allclose(g0, k["h8_cas22_grad_at_zero"], atol=3e-7)  # cell 38
+    res = minimize(lambda x: tuple(np.asarray(v) for v in O.get_energy_and_grad(x, h, 4, 2, ops, pids)), np.zeros(2), jac=True, method="L-BFGS-B")
+    assert abs(res.fun + e_core - k["h8_cas22_uccsd"]) < 1e-7  # cells 31/34
+
+
+def test_h4_adapt_vqe_pool_gradients_published():
+    """Iteration 0 of the reference's ADAPT-VQE tutorial (adapt_vqe.ipynb cell 9): 2 <HF| H G_k |HF> for every pool
+    operator of the literal H4 chain -- pins the sign convention of every excitation kind on a real molecule."""
+    from tencirchem_b200.hchain import h_chain_integrals
+
+    k = KAT["h_chain_sto3g"]
+    int1e, int2e, e_nuc, e_hf = h_chain_integrals(4)
+    assert abs(e_hf - k["h4_e_hf"]) < 1e-6
+    assert abs(np.linalg.eigvalsh(bf.dense_hamiltonian(int1e, int2e, 4))[0] + e_nuc - k["h4_e_fci"]) < 1e-6
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, 4)
+    psi = O.get_init_civector(36)
+    bra = h(psi)
+    grads = {}
+    for ops_, g_pub in k["h4_adapt_iter0"]:
+        g = 2 * sum(bra @ O.apply_excitation(psi, 8, 4, tuple(op), False) for op in ops_)
+        assert abs(g - g_pub) < 2e-7, (ops_, g, g_pub)
+        grads[str(ops_)] = g
+    singles = [2 * sum(bra @ O.apply_excitation(psi, 8, 4, op, False) for op in grp) for grp in ([(6, 4), (2, 0)], [(7, 5), (3, 1)], [(7, 4), (3, 0)], [(6, 5), (2, 1)])]
+    assert abs(np.linalg.norm(list(grads.values()) + singles) - k["h4_adapt_iter0_norm"]) < 2e-7

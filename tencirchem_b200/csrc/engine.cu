@@ -157,6 +157,8 @@ struct tcc_plan {
     bool has_h = false;
     Link* d_links = nullptr;
     double* d_w = nullptr;
+    uint16_t* d_kmap = nullptr;  // beta link (p,q) -> row of the D intermediate
+    bool w_pair_symmetric = false;
     int n2p = 0;
     uint32_t* d_ell_col = nullptr;
     double* d_ell_val = nullptr;
@@ -478,6 +480,7 @@ void tcc_plan_destroy(tcc_plan* p) {
     if (p->rot_event) cudaEventDestroy(p->rot_event);
     cudaFree(p->d_links);
     cudaFree(p->d_w);
+    cudaFree(p->d_kmap);
     cudaFree(p->d_ell_col);
     cudaFree(p->d_ell_val);
     cudaFree(p->d_strings);
@@ -575,14 +578,55 @@ int tcc_set_hamiltonian(tcc_plan* p, const double* int1e, const double* int2e) {
     if (hp.links.empty()) hp.build_links();
     hp.build_same_spin_ell(h2e);
     const int n2 = n * n;
-    p->n2p = (n2 + 3) / 4 * 4;
+    // W[pq,rs] = h2e[pq,rs] + h2e[rs,pq].  When W[pq,rs] == W[pq,sr] (true for real-orbital integrals; CHECKED here,
+    // the engine follows direct_nosym and assumes nothing) the D intermediate is folded onto pairs r <= s, which
+    // halves the K dimension of the opposite-spin GEMM.
+    std::vector<double> wfull(size_t(n2) * n2);
+    double wmax = 0.0;
+    for (int pq = 0; pq < n2; ++pq)
+        for (int rs = 0; rs < n2; ++rs) {
+            wfull[size_t(pq) * n2 + rs] = h2e[size_t(pq) * n2 + rs] + h2e[size_t(rs) * n2 + pq];
+            wmax = std::max(wmax, std::fabs(wfull[size_t(pq) * n2 + rs]));
+        }
+    bool sym = env_int("TCC_B200_SIGMA_PAIR_SYM", 1) != 0;
+    for (int pq = 0; pq < n2 && sym; ++pq)
+        for (int r = 0; r < n && sym; ++r)
+            for (int s2 = 0; s2 < r; ++s2)
+                if (std::fabs(wfull[size_t(pq) * n2 + r * n + s2] - wfull[size_t(pq) * n2 + s2 * n + r]) > 1e-14 * std::max(wmax, 1e-300)) {
+                    sym = false;
+                    break;
+                }
+    p->w_pair_symmetric = sym;
+    std::vector<uint16_t> kmap(n2);
+    int kdim = 0;
+    if (sym) {
+        std::vector<int> pair_id(n2, 0);
+        for (int r = 0; r < n; ++r)
+            for (int s2 = r; s2 < n; ++s2) pair_id[r * n + s2] = pair_id[s2 * n + r] = kdim++;
+        for (int pq = 0; pq < n2; ++pq) kmap[pq] = uint16_t(pair_id[pq]);
+    } else {
+        kdim = n2;
+        for (int p_ = 0; p_ < n; ++p_)
+            for (int q_ = 0; q_ < n; ++q_) kmap[p_ * n + q_] = uint16_t(q_ * n + p_);
+    }
+    p->n2p = (kdim + 3) / 4 * 4;
     std::vector<double> w(size_t(n2) * p->n2p, 0.0);
     for (int pq = 0; pq < n2; ++pq)
-        for (int rs = 0; rs < n2; ++rs) w[size_t(pq) * p->n2p + rs] = h2e[size_t(pq) * n2 + rs] + h2e[size_t(rs) * n2 + pq];
+        for (int r = 0; r < n; ++r)
+            for (int s2 = 0; s2 < n; ++s2) {
+                // column of W that multiplies D row kmap[(s2, r)] ... D[(q,p)] collects the forward link E_pq
+                if (sym) {
+                    if (r <= s2) w[size_t(pq) * p->n2p + kmap[r * n + s2]] = wfull[size_t(pq) * n2 + r * n + s2];
+                } else {
+                    w[size_t(pq) * p->n2p + r * n + s2] = wfull[size_t(pq) * n2 + r * n + s2];
+                }
+            }
     cudaFree(p->d_w);
     cudaFree(p->d_ell_col);
     cudaFree(p->d_ell_val);
     p->d_w = nullptr;
+    cudaFree(p->d_kmap);
+    p->d_kmap = nullptr;
     p->d_ell_col = nullptr;
     p->d_ell_val = nullptr;
     if (!p->d_links) {
@@ -591,6 +635,8 @@ int tcc_set_hamiltonian(tcc_plan* p, const double* int1e, const double* int2e) {
     }
     CUDA_TRY(dev_alloc(p, &p->d_w, w.size()));
     CUDA_TRY(cudaMemcpy(p->d_w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(dev_alloc(p, &p->d_kmap, kmap.size()));
+    CUDA_TRY(cudaMemcpy(p->d_kmap, kmap.data(), kmap.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CUDA_TRY(dev_alloc(p, &p->d_ell_col, hp.ell_col.size()));
     CUDA_TRY(dev_alloc(p, &p->d_ell_val, hp.ell_val.size()));
     CUDA_TRY(cudaMemcpy(p->d_ell_col, hp.ell_col.data(), hp.ell_col.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -623,7 +669,7 @@ static int apply_h_sets(tcc_plan* p, const double* c, double* sigma, double* ws1
     p->prof.count(TCC_PROF_SIGMA_SS, 4, 9 * vec);  // 2+2+2+3 vector passes
     // alpha-beta on the FP64 tensor path
     p->prof.mark(TCC_PROF_SIGMA_AB, st);
-    launch_sigma_ab(c, sigma, hp.na, hp.nb, p->d_links, hp.ml, p->d_w, hp.n, p->n2p, n_sets, st);
+    launch_sigma_ab(c, sigma, hp.na, hp.nb, p->d_links, hp.ml, p->d_w, hp.n, p->n2p, p->d_kmap, n_sets, st);
     p->prof.count(TCC_PROF_SIGMA_AB, (hp.na + 65534) / 65535, 3 * vec);
     p->prof.mark(-1, st);
     p->launches += 4 + (hp.na + 65534) / 65535;

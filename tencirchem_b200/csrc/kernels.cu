@@ -391,7 +391,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 
 __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict__ sigma, int64_t nb,
                                 const Link* __restrict__ links, int ml, const double* __restrict__ w, int n, int n2p,
-                                int64_t row0, int64_t set_stride) {
+                                int64_t row0, int64_t set_stride, const uint16_t* __restrict__ kmap) {
+    // n2p = K of the GEMM: n^2 (padded) in general, n(n+1)/2 (padded) when W[pq,rs] == W[pq,sr] was verified at
+    // set-up; kmap[p*n+q] = row of D that a forward beta link E_pq feeds
     extern __shared__ double dsm[];  // [n2p][SAB_LD]
     const int64_t a = row0 + blockIdx.y;
     const int64_t b0 = int64_t(blockIdx.x) * SAB_T;
@@ -407,9 +409,8 @@ __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict
         if (bp < nb) {
             Link lk = links[bp * ml + l];
             if (lk.sgn != 0) {
-                int p = lk.pq / n, q = lk.pq - p * n;
                 // forward link E_pq|b'> = sgn|b>  <=>  <b'|E_qp|b> = sgn : contributes to D[(q,p), b']
-                dsm[(q * n + p) * SAB_LD + bc] = double(lk.sgn) * __ldg(crow + lk.addr);
+                dsm[int(__ldg(kmap + lk.pq)) * SAB_LD + bc] = double(lk.sgn) * __ldg(crow + lk.addr);
             }
         }
     }
@@ -446,7 +447,7 @@ __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict
 }
 
 void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, const Link* links, int ml, const double* w,
-                     int n, int n2p, int n_sets, cudaStream_t st) {
+                     int n, int n2p, const uint16_t* kmap, int n_sets, cudaStream_t st) {
     int units = (ml / 8) * (SAB_T / 16);
     int best_nw = 4;
     double best_eff = 0.0;
@@ -469,7 +470,7 @@ void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, con
     // grid.y is limited to 65535: launch in row batches
     for (int64_t r0 = 0; r0 < gy_total; r0 += 65535) {
         unsigned gy = unsigned(gy_total - r0 < 65535 ? gy_total - r0 : 65535);
-        sigma_ab_kernel<<<dim3(gx, gy, unsigned(n_sets)), best_nw * 32, smem, st>>>(c, sigma, nb, links, ml, w, n, n2p, r0, na * nb);
+        sigma_ab_kernel<<<dim3(gx, gy, unsigned(n_sets)), best_nw * 32, smem, st>>>(c, sigma, nb, links, ml, w, n, n2p, r0, na * nb, kmap);
     }
 }
 

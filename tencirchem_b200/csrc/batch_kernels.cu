@@ -24,9 +24,10 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
 
 // per-op record resolved for the tile's (e_alpha, e_beta) at kernel start
 struct SmemOp {
-    int off, cnt;   // slice of the expanded pair list
-    double cs, sn;  // cos, sin * s0 * (spectator sign of this tile)
-    double gs;      // spectator sign of this tile: multiplies the tile's gradient partial
+    int off, cnt;    // slice of the expanded pair list
+    double cs, sn;   // cos, sin * s0
+    uint32_t smask;  // spectator sign of the excitation per class of the tile: bit g = alpha class g, bit 16 + g = beta class g
+    uint32_t pad;
 };
 
 // One rotation pass over the expanded pair list of an excitation inside the tile.  REP: the tile has a side
@@ -38,7 +39,9 @@ __device__ __forceinline__ double rotate_pairs(double* __restrict__ t0, double* 
     const int cnt = op.cnt;
     const int total = REP ? cnt * n_rep : cnt;
     if (tid >= total) return acc;
-    const double cs = op.cs, sn = op.sn;
+    // the repeat path has one class on its active side: spectator sign = bit 0 of either half of the mask
+    const bool flip = ((op.smask ^ (op.smask >> 16)) & 1u) != 0;
+    const double cs = op.cs, sn = flip ? -op.sn : op.sn;
     const uint32_t* lp = plist + op.off;
     int k = tid, base = 0, q = 0, r = 0;
     if (REP) {
@@ -78,7 +81,7 @@ __device__ __forceinline__ double rotate_pairs(double* __restrict__ t0, double* 
             k += nthreads;
         }
     }
-    return acc;
+    return flip ? -acc : acc;
 }
 
 template <int NV>
@@ -102,7 +105,7 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
     // an active side has one class per panel (G == 1); a side without active orbitals packs G single-string
     // classes, none of which is ever paired
     const int nR = int(pa.G) * int(pa.c), nC = int(pb.G) * int(pb.c);
-    const int ld = bd.B.m > 0 ? (nC | 1) : bd.ld_fixed;
+    const int ld = bd.B.m > 0 ? int(pb.ld) : bd.ld_fixed;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     double* t0 = reinterpret_cast<double*>(smem_raw);
     double* t1 = t0 + (NV == 2 ? size_t(nR) * ld : 0);
@@ -130,8 +133,19 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
         }
     }
 
-    const uint32_t sig_a = bd.A.sigma[pa.class_off];
-    const uint32_t sig_b = bd.B.sigma[pb.class_off];
+    // sub-blocks: an active side may pack G classes into the panel; each (alpha class, beta class) pair of the tile is
+    // rotated by its own group of `tps` threads with the pair list of the class pair
+    const int Ga = bd.A.m > 0 ? int(pa.G) : 1, Gb = bd.B.m > 0 ? int(pb.G) : 1;
+    const int nsub = Ga * Gb;
+    const int tps = nthreads / nsub;
+    const int sub = tid / tps;
+    const int ga = sub / Gb, gb = sub - ga * Gb;
+    // threads beyond the last sub-block never have a pair
+    const int lid = sub < nsub ? tid - sub * tps : 0x3fffffff;
+    const int wlid = __reduce_min_sync(0xffffffffu, lid);
+    const int sbase = sub < nsub ? ga * int(pa.c) * ld + gb * int(pb.c) : 0;
+    const int sshift_a = ga, sshift_b = 16 + gb;
+
     for (int t = tid; t < bd.nops; t += nthreads) {
         const BatchOp op = bd.ops[t];
         const int fwd_pos = bd.reversed ? bd.nops - 1 - t : t;
@@ -139,13 +153,16 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
         SmemOp so;
         so.off = pi[0];
         so.cnt = pi[1];
-        uint32_t sign = 0;
-        if (op.h_a >= 0) sign ^= uint32_t(__popc(sig_a & op.zspec_a));
-        if (op.h_b >= 0) sign ^= uint32_t(__popc(sig_b & op.zspec_b));
+        uint32_t smask = 0;
+        if (op.h_a >= 0)
+            for (int g = 0; g < Ga; ++g) smask |= (uint32_t(__popc(bd.A.sigma[pa.class_off + g] & op.zspec_a)) & 1u) << g;
+        if (op.h_b >= 0)
+            for (int g = 0; g < Gb; ++g) smask |= (uint32_t(__popc(bd.B.sigma[pb.class_off + g] & op.zspec_b)) & 1u) << (16 + g);
         const double2 cs = __ldg(rot + op.op_index);
         so.cs = cs.x;
-        so.sn = (sign & 1u) ? -cs.y : cs.y;
-        so.gs = (sign & 1u) ? -1.0 : 1.0;
+        so.sn = cs.y;
+        so.smask = smask;
+        so.pad = 0;
         sops[t] = so;
     }
 
@@ -198,9 +215,10 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
         const uint32_t* __restrict__ plist = bd.plist;
         uint32_t cur0[BK_DEPTH], cur1[BK_DEPTH], nxt0[BK_DEPTH], nxt1[BK_DEPTH];
         double accs[BK_DEPTH];
-        const uint32_t* __restrict__ lp0 = plist + tid;
-        const uint32_t* __restrict__ lp1 = lp0 + nthreads;
-        const int warp_first = warp << 5;
+        const uint32_t* __restrict__ lp0 = plist + (lid < 0x3fffffff ? lid : 0);
+        const uint32_t* __restrict__ lp1 = lp0 + tps;
+        double* __restrict__ s0 = t0 + sbase;
+        double* __restrict__ s1 = t1 + sbase;
         auto fetch = [&](int tbase, uint32_t* e0, uint32_t* e1) {
 #pragma unroll
             for (int j = 0; j < BK_DEPTH; ++j) {
@@ -209,27 +227,28 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
                 e1[j] = 0;
                 if (t < bd.nops) {
                     const int cnt = sops[t].cnt;
-                    if (warp_first < cnt) {  // warp-uniform: warps without pairs skip the address arithmetic too
+                    if (wlid < cnt) {  // warp-uniform: warps without pairs skip the address arithmetic too
                         const int off = sops[t].off;
-                        if (tid < cnt) e0[j] = __ldg(lp0 + off);
-                        if (tid + nthreads < cnt) e1[j] = __ldg(lp1 + off);
+                        if (lid < cnt) e0[j] = __ldg(lp0 + off);
+                        if (lid + tps < cnt) e1[j] = __ldg(lp1 + off);
                     }
                 }
             }
         };
-        auto rotate_one = [&](uint32_t e, double cs, double sn, double& acc) {
+        // sgn: spectator sign of the excitation in this thread's sub-block (0 / 1)
+        auto rotate_one = [&](uint32_t e, double cs, double sn, uint32_t sgn, double& acc) {
             const int i1 = int(e & 0x7fffu), i2 = int((e >> 15) & 0x7fffu);
-            const bool neg = (e >> 30) & 1u;
+            const bool neg = ((e >> 30) ^ sgn) & 1u;
             const double p = neg ? -sn : sn;
-            const double x = t0[i1], y = t0[i2];
+            const double x = s0[i1], y = s0[i2];
             const double nx = cs * x + p * y, ny = cs * y - p * x;
-            t0[i1] = nx;
-            t0[i2] = ny;
+            s0[i1] = nx;
+            s0[i2] = ny;
             if (NV == 2) {
-                const double bx = t1[i1], by = t1[i2];
+                const double bx = s1[i1], by = s1[i2];
                 const double nbx = cs * bx + p * by, nby = cs * by - p * bx;
-                t1[i1] = nbx;
-                t1[i2] = nby;
+                s1[i1] = nbx;
+                s1[i2] = nby;
                 const double g = nbx * ny - nby * nx;
                 acc += neg ? -g : g;
             }
@@ -243,14 +262,16 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
                 accs[j] = 0.0;
                 if (t < bd.nops) {
                     const int cnt = sops[t].cnt;
-                    if (tid < cnt) {  // warps without a pair for this excitation go straight to the barrier
+                    if (lid < cnt) {  // warps without a pair for this excitation go straight to the barrier
                         const double cs = sops[t].cs, sn = sops[t].sn;
+                        const uint32_t sm = sops[t].smask;
+                        const uint32_t sgn = (sm >> sshift_a) ^ (sm >> sshift_b);
                         double acc = 0.0;
-                        rotate_one(cur0[j], cs, sn, acc);
-                        if (tid + nthreads < cnt) {
-                            rotate_one(cur1[j], cs, sn, acc);
+                        rotate_one(cur0[j], cs, sn, sgn, acc);
+                        if (lid + tps < cnt) {
+                            rotate_one(cur1[j], cs, sn, sgn, acc);
                             const int off = sops[t].off;
-                            for (int idx = tid + 2 * nthreads; idx < cnt; idx += nthreads) rotate_one(__ldg(plist + off + idx), cs, sn, acc);
+                            for (int idx = lid + 2 * tps; idx < cnt; idx += tps) rotate_one(__ldg(plist + off + idx), cs, sn, sgn, acc);
                         }
                         accs[j] = acc;
                     }
@@ -306,7 +327,7 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
         for (int t = tid; t < bd.nops; t += nthreads) {
             double s = 0.0;
             for (int w = 0; w < nwarps; ++w) s += wpart[t * nwarps + w];
-            partials[int64_t(t) * n_tiles + tile_id] = s * sops[t].gs;
+            partials[int64_t(t) * n_tiles + tile_id] = s;
         }
     }
 }

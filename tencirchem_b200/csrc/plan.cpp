@@ -315,7 +315,7 @@ void HostPlan::build_strings() {
     }
 }
 
-void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string) {
+void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string, bool pack_classes) {
     side->S = S;
     side->m = popc(S);
     const int m = side->m;
@@ -348,19 +348,36 @@ void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool si
     side->panels.clear();
     side->max_panel = 0;
     side->max_classes = 0;
-    // panels of the largest classes first: tiles of similar size are then contiguous rectangles of the panel grid
+    // Classes per panel.  A side without active orbitals packs single-string classes up to the panel target.  On an
+    // active side the small classes (few or many active electrons) are packed 2, 4 or 8 to a panel, as long as the
+    // panel stays within the largest class: the tile count drops by a third and a tile is never mostly idle threads.
+    // The kernel applies the pair list of the class pair to each (alpha class, beta class) sub-block of the tile.
+    std::vector<int> n_cls_e(m + 1, 0), g_of_e(m + 1, 1);
+    for (size_t c = 0; c < members.size(); ++c) n_cls_e[cls_e[c]] += 1;
+    int64_t cmax = 1;
+    for (int e = 0; e <= m; ++e)
+        if (n_cls_e[e]) cmax = std::max<int64_t>(cmax, binom[m][e]);
+    side->ld_of_e.assign(m + 1, 0);
+    for (int e = 0; e <= m; ++e) {
+        if (!n_cls_e[e]) continue;
+        int g = 1;
+        if (m > 0 && pack_classes)
+            while (g * 2 <= 8 && g * 2 <= n_cls_e[e] && int64_t(g) * 2 * binom[m][e] <= cmax) g *= 2;
+        g_of_e[e] = g;
+        side->ld_of_e[e] = int(g * binom[m][e]) | 1;
+    }
+    // largest panels first: tiles of similar size are then contiguous rectangles of the panel grid
     std::vector<int> e_order;
     for (int e = 0; e <= m; ++e) e_order.push_back(e);
-    std::stable_sort(e_order.begin(), e_order.end(), [&](int x, int y) { return binom[m][x] > binom[m][y]; });
+    std::stable_sort(e_order.begin(), e_order.end(),
+                     [&](int x, int y) { return g_of_e[x] * binom[m][x] > g_of_e[y] * binom[m][y]; });
     for (int e : e_order) {
         std::vector<int> ids;
         for (size_t c = 0; c < members.size(); ++c)
             if (cls_e[c] == e) ids.push_back(int(c));
         if (ids.empty()) continue;
         const int csize = int(members[ids[0]].size());
-        // an active side keeps one class per panel (the kernels rely on it); a side without active orbitals
-        // packs single-string classes up to the panel target
-        const int per_panel = m > 0 ? 1 : std::max(1, std::min(panel_target, 4096));
+        const int per_panel = m > 0 ? g_of_e[e] : std::max(1, std::min(panel_target, 4096));
         for (size_t p0 = 0; p0 < ids.size(); p0 += per_panel) {
             size_t p1 = std::min(ids.size(), p0 + per_panel);
             PanelDesc pd;
@@ -369,7 +386,7 @@ void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool si
             pd.G = uint16_t(p1 - p0);
             pd.c = uint16_t(csize);
             pd.e = uint16_t(e);
-            pd.pad = 0;
+            pd.ld = uint16_t(side->ld_of_e[e]);
             for (size_t q = p0; q < p1; ++q) {
                 side->sigma.push_back(cls_sigma[ids[q]]);
                 for (uint32_t a : members[ids[q]]) side->addr.push_back(a);
@@ -443,8 +460,11 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
         else
             break;
     }
-    build_side(sa, int(pa), &out->A, hcb != 0);
-    build_side(sb, int(pb), &out->B, false);
+    // class packing needs hops on both sides (a side without active orbitals takes the repeat path of the kernel)
+    const bool pack = popc(sb) > 0 && (hcb || popc(sa) > 0) &&
+                      (std::getenv("TCC_B200_PACK") ? std::atoi(std::getenv("TCC_B200_PACK")) != 0 : true);
+    build_side(sa, int(pa), &out->A, hcb != 0, pack);
+    build_side(sb, int(pb), &out->B, false, pack);
     auto make_tables = [&](SideBatch& side) {
         const int m = side.m;
         std::vector<int> act;  // active orbitals sorted by storage bit position
@@ -549,7 +569,7 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
             for (int eb = 0; eb <= mb; ++eb) {
                 if (!has_eb[eb]) continue;
                 side_entries(out->B, bo.h_b, eb, &eb_list);
-                const uint32_t ld = mb > 0 ? (uint32_t(binom[mb][eb]) | 1u) : uint32_t(out->ld_fixed);
+                const uint32_t ld = mb > 0 ? uint32_t(out->B.ld_of_e[eb]) : uint32_t(out->ld_fixed);
                 const size_t slot = ((t * (ma + 1) + ea) * (mb + 1) + eb) * 2;
                 out->plist_index[slot] = int32_t(out->plist.size());
                 out->plist_index[slot + 1] = int32_t(ea_list.size() * eb_list.size());

@@ -59,7 +59,7 @@ struct PanelDesc {
     uint16_t G;          // classes in the panel
     uint16_t c;          // strings per class
     uint16_t e;          // active electrons per class
-    uint16_t pad;
+    uint16_t ld;         // leading dimension of a tile whose columns are this panel: (full G * c) | 1
 };
 
 struct LocalHop {
@@ -79,6 +79,7 @@ struct SideBatch {
     std::vector<int32_t> tab_index;    // [n_hops][m + 1][2] = (offset, count)
     int max_panel = 0;                 // largest panel (strings)
     int max_classes = 0;               // largest number of classes in a panel
+    std::vector<int> ld_of_e;          // [m + 1] tile leading dimension when this side supplies the columns
 };
 
 struct BatchOp {
@@ -92,7 +93,8 @@ struct Batch {
     SideBatch A, B;
     std::vector<BatchOp> ops;  // application order of the forward sweep
     // Fully expanded pair lists: for excitation t and a tile whose classes hold (e_a, e_b) active electrons,
-    // entries i1 | i2 << 15 | sign << 30 with i = local_row * ld + local_col (ld = tile columns | 1).
+    // entries i1 | i2 << 15 | sign << 30 with i = local_row * ld + local_col (ld = PanelDesc::ld of the beta panel),
+    // relative to the (alpha class, beta class) sub-block of the tile.
     // A side without active orbitals is not expanded: the kernel repeats the list over its rows / columns.
     std::vector<uint32_t> plist;
     std::vector<int32_t> plist_index;  // [n_ops][m_a + 1][m_b + 1][2] = (offset, count)
@@ -151,7 +153,7 @@ struct HostPlan {
     void choose_layout(const std::vector<std::vector<int>>& groups, bool use_layout);
     void build_strings();
     void build_batch(const std::vector<int>& group, int tile_elems, Batch* out);
-    void build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string);
+    void build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string, bool pack_classes);
     int64_t max_class(int m) const;
 };
 

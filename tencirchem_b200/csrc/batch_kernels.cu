@@ -146,27 +146,28 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
     const int sbase = sub < nsub ? ga * int(pa.c) * ld + gb * int(pb.c) : 0;
     const int sshift_a = ga, sshift_b = 16 + gb;
 
-    for (int t = tid; t < bd.nops; t += nthreads) {
-        const BatchOp op = bd.ops[t];
-        const int fwd_pos = bd.reversed ? bd.nops - 1 - t : t;
-        const int* pi = bd.plist_index + ((size_t(fwd_pos) * (bd.A.m + 1) + int(pa.e)) * (bd.B.m + 1) + int(pb.e)) * 2;
-        SmemOp so;
-        so.off = pi[0];
-        so.cnt = pi[1];
-        uint32_t smask = 0;
-        if (op.h_a >= 0)
-            for (int g = 0; g < Ga; ++g) smask |= (uint32_t(__popc(bd.A.sigma[pa.class_off + g] & op.zspec_a)) & 1u) << g;
-        if (op.h_b >= 0)
-            for (int g = 0; g < Gb; ++g) smask |= (uint32_t(__popc(bd.B.sigma[pb.class_off + g] & op.zspec_b)) & 1u) << (16 + g);
-        const double2 cs = __ldg(rot + op.op_index);
-        so.cs = cs.x;
-        so.sn = cs.y;
-        so.smask = smask;
-        so.pad = 0;
-        sops[t] = so;
-    }
-
-    __syncthreads();  // row_addr, sops
+    auto setup_ops = [&]() {
+        for (int t = tid; t < bd.nops; t += nthreads) {
+            const BatchOp op = bd.ops[t];
+            const int fwd_pos = bd.reversed ? bd.nops - 1 - t : t;
+            const int* pi = bd.plist_index + ((size_t(fwd_pos) * (bd.A.m + 1) + int(pa.e)) * (bd.B.m + 1) + int(pb.e)) * 2;
+            SmemOp so;
+            so.off = pi[0];
+            so.cnt = pi[1];
+            uint32_t smask = 0;
+            if (op.h_a >= 0)
+                for (int g = 0; g < Ga; ++g) smask |= (uint32_t(__popc(bd.A.sigma[pa.class_off + g] & op.zspec_a)) & 1u) << g;
+            if (op.h_b >= 0)
+                for (int g = 0; g < Gb; ++g) smask |= (uint32_t(__popc(bd.B.sigma[pb.class_off + g] & op.zspec_b)) & 1u) << (16 + g);
+            const double2 cs = __ldg(rot + op.op_index);
+            so.cs = cs.x;
+            so.sn = cs.y;
+            so.smask = smask;
+            so.pad = 0;
+            sops[t] = so;
+        }
+    };
+    __syncthreads();  // row_addr
     // ---- gather the tile
     if (reg_cols) {
         // asynchronous global->shared copies (LDGSTS): every element of the tile is in flight before the first
@@ -180,8 +181,10 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
                     if (NV == 2) cp_async8(t1 + lr * ld + lcs[j], v1 + ra + colg[j]);
                 }
         }
+        setup_ops();  // the dependent global loads of the op records overlap the gather
         asm volatile("cp.async.wait_all;\n" ::: "memory");
     } else {
+        setup_ops();
         for (int lr = warp; lr < nR; lr += nwarps) {
             const int64_t row = int64_t(row_addr[lr]) * nb;
             for (int t = lane; t < nC; t += 32) {
@@ -368,22 +371,74 @@ cudaError_t batch_kernels_configure() {
     return cudaFuncSetAttribute(batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
-void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                          int threads, int n_sets, SetStrides ss, cudaStream_t st) {
-    for (const TileRect& r : rects) {
-        dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
-        batch_kernel<1><<<grid, threads, r.smem_fwd, st>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss, r);
+cudaError_t StreamFan::create(int n_aux) {
+    cudaError_t e = cudaEventCreateWithFlags(&start, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < n_aux; ++i) {
+        cudaStream_t s;
+        cudaEvent_t ev;
+        if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        aux.push_back(s);
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        done.push_back(ev);
     }
+    return cudaSuccess;
+}
+
+void StreamFan::destroy() {
+    for (auto s : aux) cudaStreamDestroy(s);
+    for (auto e : done) cudaEventDestroy(e);
+    if (start) cudaEventDestroy(start);
+    aux.clear();
+    done.clear();
+    start = nullptr;
+}
+
+// runs launch(rect, stream) for every rectangle: the first on `st`, the others on the auxiliary streams between a
+// fork and a join event (serially on `st` without a fan)
+template <class F>
+static void fan_out(const std::vector<TileRect>& rects, cudaStream_t st, StreamFan* fan, F launch) {
+    const size_t n = rects.size();
+    if (!fan || n < 2 || fan->aux.empty()) {
+        for (const TileRect& r : rects) launch(r, st);
+        return;
+    }
+    const size_t n_aux = fan->aux.size();
+    cudaEventRecord(fan->start, st);
+    std::vector<char> used(n_aux, 0);
+    for (size_t i = 0; i < n; ++i) {
+        if (i == 0) {
+            launch(rects[i], st);
+            continue;
+        }
+        const size_t k = (i - 1) % n_aux;
+        if (!used[k]) cudaStreamWaitEvent(fan->aux[k], fan->start, 0);
+        used[k] = 1;
+        launch(rects[i], fan->aux[k]);
+    }
+    for (size_t k = 0; k < n_aux; ++k)
+        if (used[k]) {
+            cudaEventRecord(fan->done[k], fan->aux[k]);
+            cudaStreamWaitEvent(st, fan->done[k], 0);
+        }
+}
+
+void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
+                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan) {
+    fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
+        dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
+        batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss, r);
+    });
 }
 
 void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot,
                           const std::vector<TileRect>& rects, int threads, double* partials, double* grad_ops, int n_sets,
-                          SetStrides ss, cudaStream_t st) {
+                          SetStrides ss, cudaStream_t st, StreamFan* fan) {
     const int n_tiles = bd.B.n_panels * bd.A.n_panels;
-    for (const TileRect& r : rects) {
+    fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
-        batch_kernel<2><<<grid, threads, r.smem_rev, st>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss, r);
-    }
+        batch_kernel<2><<<grid, threads, r.smem_rev, s>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss, r);
+    });
     batch_grad_reduce_kernel<<<dim3(bd.nops, unsigned(n_sets), 1), 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops, ss);
 }
 

@@ -46,13 +46,23 @@ struct TileRect {
     size_t smem_fwd, smem_rev;
 };
 
+// Auxiliary streams for the rectangle launches of one batch: the rectangles are independent sets of tiles, so they
+// run concurrently (fork from / join into the caller's stream with events) and fill each other's tails.
+struct StreamFan {
+    std::vector<cudaStream_t> aux;
+    std::vector<cudaEvent_t> done;
+    cudaEvent_t start = nullptr;
+    cudaError_t create(int n_aux);
+    void destroy();
+};
+
 cudaError_t batch_kernels_configure();
 size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv);
 void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                          int threads, int n_sets, SetStrides ss, cudaStream_t st);
+                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan);
 void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot,
                           const std::vector<TileRect>& rects, int threads, double* partials, double* grad_ops, int n_sets,
-                          SetStrides ss, cudaStream_t st);
+                          SetStrides ss, cudaStream_t st, StreamFan* fan);
 void launch_permute(const double* in, double* out, int64_t na, int64_t nb, const uint32_t* map_a, const uint32_t* map_b,
                     cudaStream_t st);
 

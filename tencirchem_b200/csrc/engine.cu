@@ -104,7 +104,8 @@ struct BatchDevSet {
     int n_tiles = 0;
     int nops = 0;
     int max_rows = 0, max_cols = 0;
-    std::vector<TileRect> rects;
+    std::vector<TileRect> rects;      // forward launches
+    std::vector<TileRect> rects_rev;  // reverse launches
     std::vector<void*> allocs;
 };
 
@@ -151,6 +152,7 @@ struct tcc_plan {
     double2* d_rot_rev = nullptr;  // [n_ops] (cos, -sin * s0)
     double2* h_rot = nullptr;      // pinned [2 * n_ops]
     cudaEvent_t rot_event = nullptr;
+    StreamFan fan;  // concurrent rectangle launches of a batch
     uint32_t* d_ref2int = nullptr;
     uint32_t* d_int2ref = nullptr;
     int64_t hf_index = 0;
@@ -251,40 +253,54 @@ static int upload_batches(tcc_plan* p) {
         auto side_ranges = [](const SideBatch& sb) {
             std::vector<std::array<int, 3>> out;  // lo, count, max panel size
             const int np_ = int(sb.panels.size());
+            // nominal size of a panel: the full panel of its electron count (a last, partly filled panel counts as full)
+            auto nominal = [&](int i) {
+                return sb.m > 0 ? int(sb.panels[i].ld) : int(sb.panels[i].G) * int(sb.panels[i].c);
+            };
             int lo = 0;
             while (lo < np_) {
-                const int big = int(sb.panels[lo].G) * int(sb.panels[lo].c);
+                int big = nominal(lo);
                 int hi = lo + 1;
-                // a range ends when the panels get smaller than 3/4 of its first (largest) one; at most 3 ranges
-                while (hi < np_ && (int(out.size()) == 2 || 4 * int(sb.panels[hi].G) * int(sb.panels[hi].c) >= 3 * big)) ++hi;
+                // a range ends when the panels get smaller than 85 % of its first (largest) one; at most 3 ranges
+                while (hi < np_ && (int(out.size()) == 2 || 100 * nominal(hi) >= 85 * big)) {
+                    big = std::max(big, nominal(hi));
+                    ++hi;
+                }
                 out.push_back({lo, hi - lo, big});
                 lo = hi;
             }
             return out;
         };
-        const int split = env_int("TCC_B200_TILE_RECTS", 0);  // measured: +17 ms forward, -17 ms reverse at (16e,16o): off by default
-        std::vector<std::array<int, 3>> ra = side_ranges(hb.A), rb = side_ranges(hb.B);
-        if (!split) {
-            ra = {{0, int(hb.A.panels.size()), hb.A.max_panel}};
-            rb = {{0, int(hb.B.panels.size()), hb.B.max_panel}};
-        }
-        db.rects.clear();
+        // 0 (default): one launch per batch; 1: the reverse kernel, whose occupancy is bound by shared memory (ket and
+        // bra tile), gets one launch per rectangle; 2: the forward kernel too.  Measured at (16e,16o): the per-excitation
+        // cost of the reverse kernel drops by 25 % but the per-batch cost grows more (tiles that share DRAM sectors no
+        // longer run together), see profiles/r01_batch_kernel_experiments.md
+        const int split = env_int("TCC_B200_TILE_RECTS", 0);
+        const std::vector<std::array<int, 3>> one_a = {{0, int(hb.A.panels.size()), hb.A.max_panel}};
+        const std::vector<std::array<int, 3>> one_b = {{0, int(hb.B.panels.size()), hb.B.max_panel}};
         db.smem_fwd = db.smem_rev = 0;
-        for (auto& xa : ra)
-            for (auto& xb : rb) {
-                TileRect r;
-                r.pa_lo = xa[0];
-                r.pa_cnt = xa[1];
-                r.pb_lo = xb[0];
-                r.pb_cnt = xb[1];
-                // ld of a tile is (columns | 1) except when the beta side has no active orbitals (fixed ld)
-                const int cols = hb.B.m > 0 ? xb[2] : hb.B.max_panel;
-                r.smem_fwd = batch_smem_bytes(xa[2], cols, db.nops, 1);
-                r.smem_rev = batch_smem_bytes(xa[2], cols, db.nops, 2);
-                db.smem_fwd = std::max(db.smem_fwd, r.smem_fwd);
-                db.smem_rev = std::max(db.smem_rev, r.smem_rev);
-                if (r.pa_cnt > 0 && r.pb_cnt > 0) db.rects.push_back(r);
-            }
+        auto make_rects = [&](bool do_split, std::vector<TileRect>* out) {
+            const std::vector<std::array<int, 3>> ra = do_split ? side_ranges(hb.A) : one_a;
+            const std::vector<std::array<int, 3>> rb = do_split ? side_ranges(hb.B) : one_b;
+            out->clear();
+            for (auto& xa : ra)
+                for (auto& xb : rb) {
+                    TileRect r;
+                    r.pa_lo = xa[0];
+                    r.pa_cnt = xa[1];
+                    r.pb_lo = xb[0];
+                    r.pb_cnt = xb[1];
+                    // ld of a tile follows its beta panel except when the beta side has no active orbitals (fixed ld)
+                    const int cols = hb.B.m > 0 ? xb[2] : hb.B.max_panel;
+                    r.smem_fwd = batch_smem_bytes(xa[2], cols, db.nops, 1);
+                    r.smem_rev = batch_smem_bytes(xa[2], cols, db.nops, 2);
+                    db.smem_fwd = std::max(db.smem_fwd, r.smem_fwd);
+                    db.smem_rev = std::max(db.smem_rev, r.smem_rev);
+                    if (r.pa_cnt > 0 && r.pb_cnt > 0) out->push_back(r);
+                }
+        };
+        make_rects(split >= 2, &db.rects);
+        make_rects(split >= 1, &db.rects_rev);
         if (db.smem_rev > 232448)
             return fail(TCC_ERR_BAD_ARGUMENT, "batch tile does not fit in shared memory: lower TCC_B200_TILE_ELEMS");
         max_part = std::max(max_part, size_t(db.nops) * size_t(db.n_tiles));
@@ -428,7 +444,8 @@ int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t*
         cudaMalloc(&p->d_int2ref, sizeof(uint32_t) * p->hp.nstr) != cudaSuccess ||
         cudaMallocHost(&p->h_rot, sizeof(double2) * (2 * n_ops + 2)) != cudaSuccess ||
         cudaMallocHost(&p->pinned, sizeof(double) * (n_ops + 8)) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p->rot_event, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&p->rot_event, cudaEventDisableTiming) != cudaSuccess ||
+        p->fan.create(env_int("TCC_B200_FAN_STREAMS", 8)) != cudaSuccess) {
         g_error = std::string("plan workspace allocation: ") + cudaGetErrorString(cudaGetLastError());
         return bail(TCC_ERR_CUDA);
     }
@@ -478,6 +495,7 @@ void tcc_plan_destroy(tcc_plan* p) {
     if (p->h_rot) cudaFreeHost(p->h_rot);
     if (p->pinned) cudaFreeHost(p->pinned);
     if (p->rot_event) cudaEventDestroy(p->rot_event);
+    p->fan.destroy();
     cudaFree(p->d_links);
     cudaFree(p->d_w);
     cudaFree(p->d_kmap);
@@ -732,7 +750,7 @@ static int forward_sweep(tcc_plan* p, const double* params, double* vec, cudaStr
         for (size_t b = 0; b < nbt; ++b) {
             BatchDevSet& db = p->dbatches[b];
             if (p->btimer.on) cudaEventRecord(p->btimer.ev[b], st);
-            launch_batch_forward(vec, hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st);
+            launch_batch_forward(vec, hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
             p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * hp.N);
             p->launches += 1;
         }
@@ -754,8 +772,8 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
         for (int b = nbt - 1; b >= 0; --b) {
             BatchDevSet& db = p->dbatches[b];
             if (p->btimer.on) cudaEventRecord(p->btimer.ev[nbt + 1 + (nbt - 1 - b)], st);
-            launch_batch_reverse(ket, bra, hp.nb, db.rev, p->d_rot_rev, db.rects, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
-                                 SetStrides{0, 0, 0, 0}, st);
+            launch_batch_reverse(ket, bra, hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
+                                 SetStrides{0, 0, 0, 0}, st, &p->fan);
             p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * hp.N);  // the tiny gradient-reduce launch rides along
             p->launches += 2;
         }
@@ -970,7 +988,7 @@ int tcc_energy_and_grad_batch(tcc_plan* p, int n_sets, const double* params_host
         p->launches += 1;
         for (auto& db : p->dbatches) {
             launch_batch_forward(ws.ket, hp.nb, db.fwd, ws.rot_fwd, db.rects, p->batch_threads, ns,
-                                 SetStrides{hp.N, m, 0, 0}, st);
+                                 SetStrides{hp.N, m, 0, 0}, st, &p->fan);
             p->launches += 1;
         }
         if (int rc = apply_h_sets(p, ws.ket, ws.bra, ws.ws1, ws.ws2, ns, st)) return rc;
@@ -979,8 +997,8 @@ int tcc_energy_and_grad_batch(tcc_plan* p, int n_sets, const double* params_host
         if (grads_host) {
             for (int b = int(p->dbatches.size()) - 1; b >= 0; --b) {
                 BatchDevSet& db = p->dbatches[b];
-                launch_batch_reverse(ws.ket, ws.bra, hp.nb, db.rev, ws.rot_rev, db.rects, p->batch_threads_rev, ws.bpart, ws.grad, ns,
-                                     SetStrides{hp.N, m, int64_t(max_part), m + 1}, st);
+                launch_batch_reverse(ws.ket, ws.bra, hp.nb, db.rev, ws.rot_rev, db.rects_rev, p->batch_threads_rev, ws.bpart, ws.grad, ns,
+                                     SetStrides{hp.N, m, int64_t(max_part), m + 1}, st, &p->fan);
                 p->launches += 2;
             }
         }

@@ -22,6 +22,14 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
 
+// shared-memory accesses by 32-bit shared-window address: no generic-address arithmetic in the excitation loop
+__device__ __forceinline__ double lds64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v) : "memory"); }
+
 // per-op record resolved for the tile's (e_alpha, e_beta) at kernel start
 struct SmemOp {
     int off, cnt;    // slice of the expanded pair list
@@ -238,23 +246,28 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
                 }
             }
         };
-        // sgn: spectator sign of the excitation in this thread's sub-block (0 / 1)
-        auto rotate_one = [&](uint32_t e, double cs, double sn, uint32_t sgn, double& acc) {
-            const int i1 = int(e & 0x7fffu), i2 = int((e >> 15) & 0x7fffu);
-            const bool neg = ((e >> 30) ^ sgn) & 1u;
-            const double p = neg ? -sn : sn;
-            const double x = s0[i1], y = s0[i2];
-            const double nx = cs * x + p * y, ny = cs * y - p * x;
-            s0[i1] = nx;
-            s0[i2] = ny;
+        const uint32_t sh0 = uint32_t(__cvta_generic_to_shared(s0));
+        const uint32_t sh1 = uint32_t(__cvta_generic_to_shared(s1));
+        // sflip: the sub-block's spectator sign of the excitation as an FP64 sign bit; together with the pair's own
+        // sign (bit 30 of the entry) it is XORed into the high word of the sine and of the gradient term: no FP64
+        // negate / select
+        auto rotate_one = [&](uint32_t e, double cs, double sn, uint32_t sflip, double& acc) {
+            const uint32_t o1 = (e & 0x7fffu) << 3, o2 = (e >> 12) & 0x3fff8u;
+            const uint32_t flip = ((e << 1) & 0x80000000u) ^ sflip;
+            const double p = __hiloint2double(__double2hiint(sn) ^ int(flip), __double2loint(sn));
+            const double x = lds64(sh0 + o1), y = lds64(sh0 + o2);
             if (NV == 2) {
-                const double bx = s1[i1], by = s1[i2];
+                const double bx = lds64(sh1 + o1), by = lds64(sh1 + o2);
                 const double nbx = cs * bx + p * by, nby = cs * by - p * bx;
-                s1[i1] = nbx;
-                s1[i2] = nby;
-                const double g = nbx * ny - nby * nx;
-                acc += neg ? -g : g;
+                // <bra|G|ket> of the pair, invariant under the common rotation: taken from the values before it
+                const double g = bx * y - by * x;
+                acc += __hiloint2double(__double2hiint(g) ^ int(flip), __double2loint(g));
+                sts64(sh1 + o1, nbx);
+                sts64(sh1 + o2, nby);
             }
+            const double nx = cs * x + p * y, ny = cs * y - p * x;
+            sts64(sh0 + o1, nx);
+            sts64(sh0 + o2, ny);
         };
         fetch(0, cur0, cur1);
         for (int tb = 0; tb < bd.nops; tb += BK_DEPTH) {
@@ -268,7 +281,7 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
                     if (lid < cnt) {  // warps without a pair for this excitation go straight to the barrier
                         const double cs = sops[t].cs, sn = sops[t].sn;
                         const uint32_t sm = sops[t].smask;
-                        const uint32_t sgn = (sm >> sshift_a) ^ (sm >> sshift_b);
+                        const uint32_t sgn = ((sm >> sshift_a) ^ (sm >> sshift_b)) << 31;
                         double acc = 0.0;
                         rotate_one(cur0[j], cs, sn, sgn, acc);
                         if (lid + tps < cnt) {

@@ -274,14 +274,14 @@ static int upload_batches(tcc_plan* p) {
         // 0 (default): one launch per batch; 1: the reverse kernel, whose occupancy is bound by shared memory (ket and
         // bra tile), gets one launch per rectangle; 2: the forward kernel too.  Measured at (16e,16o): the per-excitation
         // cost of the reverse kernel drops by 25 % but the per-batch cost grows more (tiles that share DRAM sectors no
-        // longer run together), see profiles/r01_batch_kernel_experiments.md
+        // longer run together), see profiles/r01_batch_kernel_experiments.md.  3: reverse kernel, split along alpha only
         const int split = env_int("TCC_B200_TILE_RECTS", 0);
         const std::vector<std::array<int, 3>> one_a = {{0, int(hb.A.panels.size()), hb.A.max_panel}};
         const std::vector<std::array<int, 3>> one_b = {{0, int(hb.B.panels.size()), hb.B.max_panel}};
         db.smem_fwd = db.smem_rev = 0;
         auto make_rects = [&](bool do_split, std::vector<TileRect>* out) {
             const std::vector<std::array<int, 3>> ra = do_split ? side_ranges(hb.A) : one_a;
-            const std::vector<std::array<int, 3>> rb = do_split ? side_ranges(hb.B) : one_b;
+            const std::vector<std::array<int, 3>> rb = do_split && split != 3 ? side_ranges(hb.B) : one_b;
             out->clear();
             for (auto& xa : ra)
                 for (auto& xb : rb) {

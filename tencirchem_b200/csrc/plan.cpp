@@ -349,7 +349,8 @@ void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool si
     side->max_panel = 0;
     side->max_classes = 0;
     // Classes per panel.  A side without active orbitals packs single-string classes up to the panel target.  On an
-    // active side the small classes (few or many active electrons) are packed 2, 4 or 8 to a panel, as long as the
+    // active side the small classes (few or many active electrons) are packed 2 or 4 to a panel (at most 16 sub-blocks
+    // per tile, each with its own group of threads of the CTA), as long as the
     // panel stays within the largest class: the tile count drops by a third and a tile is never mostly idle threads.
     // The kernel applies the pair list of the class pair to each (alpha class, beta class) sub-block of the tile.
     std::vector<int> n_cls_e(m + 1, 0), g_of_e(m + 1, 1);
@@ -362,7 +363,7 @@ void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool si
         if (!n_cls_e[e]) continue;
         int g = 1;
         if (m > 0 && pack_classes)
-            while (g * 2 <= 8 && g * 2 <= n_cls_e[e] && int64_t(g) * 2 * binom[m][e] <= cmax) g *= 2;
+            while (g * 2 <= 4 && g * 2 <= n_cls_e[e] && int64_t(g) * 2 * binom[m][e] <= cmax) g *= 2;
         g_of_e[e] = g;
         side->ld_of_e[e] = int(g * binom[m][e]) | 1;
     }

@@ -141,6 +141,37 @@ int64_t tcc_op_support_bytes(const tcc_plan* plan, int j);
 /* kernel launches issued by this plan since creation (for bench.py's gpu_launches) */
 int64_t tcc_launch_count(const tcc_plan* plan);
 
+/* ---- multi-GPU: alpha-row sharded plans -----------------------------
+ * The [na, nb] CI matrix is split by alpha rows over `world` ranks (one process per GPU, world a power of
+ * two).  A rank owns the rows whose occupation pattern on `t = log2(world)` alpha orbitals T equals its rank;
+ * T is chosen per batch among the orbitals that are NOT active on the alpha side of the batch, so every tile
+ * of the batch lies on one rank and the batch kernels run on the local [rows, nb] matrix without any
+ * communication.  Consecutive batches with the same T form a segment; between segments the caller moves rows
+ * between ranks (all-to-all; tencirchem_b200/sharded.py does it with torch.distributed over NCCL).
+ * Replaces the single-process loops of evolve_civector.py:165-177 / :221-243 for vectors that exceed one GPU. */
+int tcc_plan_create_sharded(int n_qubits, int n_elec, int n_ops, const int32_t* ex_ops_flat,
+                            const int32_t* ex_op_len, const int32_t* param_ids, int device, int rank, int world,
+                            tcc_plan** out);
+int tcc_shard_info(const tcc_plan* plan, int32_t* rank, int32_t* world, int32_t* n_layouts, int32_t* n_segments,
+                   int64_t* max_local_rows);
+int tcc_shard_segment(const tcc_plan* plan, int seg, int32_t* layout, int32_t* batch_lo, int32_t* batch_hi);
+/* owner_host[a] = rank that owns storage row a in this layout (local rows ascend with a); orbital_mask = T */
+int tcc_shard_layout(const tcc_plan* plan, int layout, int32_t* owner_host /* [num_strings] */,
+                     uint32_t* orbital_mask);
+/* uploads cos / sin of every factor and clears the gradient accumulators: once per evaluation */
+int tcc_shard_set_params(tcc_plan* plan, const double* params_host, void* stream);
+/* all batches of segment `seg` on the local rows (storage order, layout of the segment) */
+int tcc_shard_forward(tcc_plan* plan, int seg, double* vec_local_dev, void* stream);
+int tcc_shard_reverse(tcc_plan* plan, int seg, double* ket_local_dev, double* bra_local_dev, void* stream);
+/* this rank's share of 2 * <bra|G_j|ket> summed by parameter; the caller adds the shares (all-reduce) */
+int tcc_shard_gradient(tcc_plan* plan, double* grad_host /* [num_params] */, void* stream);
+/* Contributions to sigma = H c of the storage rows [row_lo, row_lo + row_cnt): same-spin terms of these rows and
+ * opposite-spin terms scattered from them, ADDED into sigma_full_dev.  Full [na, nb] storage-order matrices; the
+ * sum over any partition of the rows is H c (hamiltonian.py:146-155), so ranks split the work by row blocks and
+ * all-reduce. */
+int tcc_apply_h_rows(tcc_plan* plan, const double* c_full_dev, double* sigma_full_dev, int64_t row_lo,
+                     int64_t row_cnt, void* stream);
+
 /* ---- per-phase device timing (CUDA events on the call's stream, recorded only where the phase
  * changes).  Slots: forward rotations by kind, reverse-sweep steps by kind, the same-spin and
  * opposite-spin parts of H.c, the energy dot product.  `bytes` are ALGORITHMIC CI-vector bytes

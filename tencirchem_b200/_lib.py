@@ -57,6 +57,15 @@ SIGNATURES = {
     "tcc_reverse_step": (C.c_int, [_p, C.c_int, C.c_double, _p, _p, _p, _p]),
     "tcc_op_support_bytes": (C.c_int64, [_p, C.c_int]),
     "tcc_launch_count": (C.c_int64, [_p]),
+    "tcc_plan_create_sharded": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
+    "tcc_shard_info": (C.c_int, [_p, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
+    "tcc_shard_segment": (C.c_int, [_p, C.c_int, _ip, _ip, _ip]),
+    "tcc_shard_layout": (C.c_int, [_p, C.c_int, _ip, C.POINTER(C.c_uint32)]),
+    "tcc_shard_set_params": (C.c_int, [_p, _dp, _p]),
+    "tcc_shard_forward": (C.c_int, [_p, C.c_int, _p, _p]),
+    "tcc_shard_reverse": (C.c_int, [_p, C.c_int, _p, _p, _p]),
+    "tcc_shard_gradient": (C.c_int, [_p, _dp, _p]),
+    "tcc_apply_h_rows": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, _p]),
     "tcc_profile_enable": (C.c_int, [_p, C.c_int]),
     "tcc_profile_read": (C.c_int, [_p, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tcc_profile_batches": (C.c_int, [_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -440,6 +440,7 @@ void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const doubl
                           int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan) {
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
+        if (grid.x == 0) return;  // a rank of a sharded plan may own no class of this batch
         batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss, r);
     });
 }
@@ -450,6 +451,7 @@ void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& 
     const int n_tiles = bd.B.n_panels * bd.A.n_panels;
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
+        if (grid.x == 0) return;
         batch_kernel<2><<<grid, threads, r.smem_rev, s>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss, r);
     });
     batch_grad_reduce_kernel<<<dim3(bd.nops, unsigned(n_sets), 1), 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops, ss);

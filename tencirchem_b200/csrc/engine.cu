@@ -159,6 +159,8 @@ struct tcc_plan {
     bool has_h = false;
     Link* d_links = nullptr;
     double* d_w = nullptr;
+    double *rows_ws1 = nullptr, *rows_ws2 = nullptr;  // scratch of tcc_apply_h_rows
+    size_t rows_ws_cap = 0;
     uint16_t* d_kmap = nullptr;  // beta link (p,q) -> row of the D intermediate
     bool w_pair_symmetric = false;
     int n2p = 0;
@@ -334,6 +336,13 @@ static int use_device(const tcc_plan* p) {
     return 0;
 }
 
+// the whole-vector entry points of a plan that holds only a block of alpha rows make no sense
+static int whole_vector_only(const tcc_plan* p) {
+    if (p->hp.shard_world > 1)
+        return fail(TCC_ERR_BAD_ARGUMENT, "sharded plan: use the tcc_shard_* entry points (the plan holds 1/world of the rows)");
+    return 0;
+}
+
 
 // reference order -> storage order and back (vectors crossing the ABI are in reference order)
 static void to_storage(tcc_plan* p, const double* ref, double* st_vec, cudaStream_t st) {
@@ -367,10 +376,13 @@ int tcc_device_count(void) {
     return n;
 }
 
-int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t* ex_ops_flat, const int32_t* ex_op_len,
-                    const int32_t* param_ids, int device, tcc_plan** out) {
+static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t* ex_ops_flat, const int32_t* ex_op_len,
+                            const int32_t* param_ids, int device, int rank, int world, tcc_plan** out) {
     if (!out) return fail(TCC_ERR_BAD_ARGUMENT, "out is null");
     *out = nullptr;
+    if (world < 1 || (world & (world - 1)) || world > 64 || rank < 0 || rank >= world)
+        return fail(TCC_ERR_BAD_ARGUMENT, "world size must be a power of two (<= 64) and 0 <= rank < world");
+    if (world > 1 && hcb) return fail(TCC_ERR_BAD_ARGUMENT, "hcb plans have a single alpha row and are not sharded");
     if (n_ops < 0 || (n_ops > 0 && (!ex_ops_flat || !ex_op_len))) return fail(TCC_ERR_BAD_ARGUMENT, "bad excitation list");
     tcc_plan* p = new tcc_plan();
     int rc = p->hp.init(n_qubits, n_elec, hcb);
@@ -405,7 +417,14 @@ int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t*
     p->mode = env_int("TCC_B200_PER_OP", 0) ? 1 : 0;
     p->batch_threads = std::min(256, std::max(32, env_int("TCC_B200_BATCH_THREADS", 256) / 32 * 32));
     p->batch_threads_rev = std::min(256, std::max(32, env_int("TCC_B200_BATCH_THREADS_REV", p->batch_threads) / 32 * 32));
-    p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0);
+    if (world > 1) p->mode = 0;  // sharded plans run the batched engine only
+    p->hp.error.clear();
+    p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0, rank, world);
+    if (!p->hp.error.empty()) {
+        g_error = p->hp.error;
+        delete p;
+        return TCC_ERR_BAD_ARGUMENT;
+    }
     {
         uint32_t hf = p->hp.k ? ((1u << p->hp.k) - 1) : 0u;
         int64_t r = p->hp.rank(hf);
@@ -458,6 +477,16 @@ int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t*
     return 0;
 }
 
+int tcc_plan_create(int n_qubits, int n_elec, int hcb, int n_ops, const int32_t* ex_ops_flat, const int32_t* ex_op_len,
+                    const int32_t* param_ids, int device, tcc_plan** out) {
+    return plan_create_impl(n_qubits, n_elec, hcb, n_ops, ex_ops_flat, ex_op_len, param_ids, device, 0, 1, out);
+}
+
+int tcc_plan_create_sharded(int n_qubits, int n_elec, int n_ops, const int32_t* ex_ops_flat, const int32_t* ex_op_len,
+                            const int32_t* param_ids, int device, int rank, int world, tcc_plan** out) {
+    return plan_create_impl(n_qubits, n_elec, 0, n_ops, ex_ops_flat, ex_op_len, param_ids, device, rank, world, out);
+}
+
 static void free_sets_ws(tcc_plan* p);
 
 void tcc_plan_destroy(tcc_plan* p) {
@@ -498,6 +527,8 @@ void tcc_plan_destroy(tcc_plan* p) {
     p->fan.destroy();
     cudaFree(p->d_links);
     cudaFree(p->d_w);
+    cudaFree(p->rows_ws1);
+    cudaFree(p->rows_ws2);
     cudaFree(p->d_kmap);
     cudaFree(p->d_ell_col);
     cudaFree(p->d_ell_val);
@@ -816,6 +847,7 @@ int tcc_apply_h(tcc_plan* p, const double* c_dev, double* sigma_dev, void* strea
 int tcc_civector(tcc_plan* p, const double* params_host, const double* init_dev, double* out_dev, void* stream) {
     if (!p || !out_dev || (!params_host && p->hp.n_params > 0)) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
     cudaStream_t st = cudaStream_t(stream);
     if (p->hp.identity_layout) {
         if (int rc = prepare_state(p, params_host, init_dev, out_dev, st)) return rc;
@@ -848,6 +880,7 @@ int tcc_rotate(tcc_plan* p, int j, double theta, double* c_dev, void* stream) {
     if (!p || !c_dev) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (j < 0 || j >= int(p->hp.ops.size())) return fail(TCC_ERR_BAD_ARGUMENT, "excitation index out of range");
     if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
     rotate_op(p, j, theta, c_dev, cudaStream_t(stream));
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -857,6 +890,7 @@ int tcc_reverse_step(tcc_plan* p, int j, double theta, double* ket_dev, double* 
     if (!p || !ket_dev || !bra_dev || !grad_dev) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (j < 0 || j >= int(p->hp.ops.size())) return fail(TCC_ERR_BAD_ARGUMENT, "excitation index out of range");
     if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
     reverse_op(p, j, theta, ket_dev, bra_dev, grad_dev, cudaStream_t(stream));
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -895,6 +929,7 @@ static int energy_impl(tcc_plan* p, const double* params, const double* init_dev
 int tcc_energy(tcc_plan* p, const double* params_host, const double* init_dev, double* energy_host, void* stream) {
     if (!p || !energy_host || (!params_host && p->hp.n_params > 0)) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
     return energy_impl(p, params_host, init_dev, energy_host, nullptr, cudaStream_t(stream));
 }
 
@@ -902,6 +937,7 @@ int tcc_energy_and_grad(tcc_plan* p, const double* params_host, const double* in
                         double* grad_host, void* stream) {
     if (!p || !energy_host || !grad_host || (!params_host && p->hp.n_params > 0)) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
     return energy_impl(p, params_host, init_dev, energy_host, grad_host, cudaStream_t(stream));
 }
 
@@ -937,6 +973,7 @@ int tcc_energy_and_grad_batch(tcc_plan* p, int n_sets, const double* params_host
     if (!p || n_sets < 0 || !energies_host || (!params_host && p->hp.n_params > 0 && n_sets > 0))
         return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
     HostPlan& hp = p->hp;
     if (!p->has_h) return fail(TCC_ERR_NO_HAMILTONIAN, "tcc_set_hamiltonian has not been called");
     if (n_sets == 0) return 0;
@@ -1056,6 +1093,145 @@ int tcc_profile_enable(tcc_plan* p, int on) {
     return 0;
 }
 
+// ---- alpha-row sharded plans --------------------------------------------------------------------
+// Every rank builds the same schedule; its alpha side holds only the rows the rank owns in the layout of each
+// batch, addressed by local row, so the batch kernels run unchanged on the local [rows, nb] matrix.  Between
+// segments (runs of batches with one layout) the caller moves rows between ranks (all-to-all).
+int tcc_shard_info(const tcc_plan* p, int32_t* rank, int32_t* world, int32_t* n_layouts, int32_t* n_segments,
+                   int64_t* max_local_rows) {
+    if (!p) return fail(TCC_ERR_BAD_ARGUMENT, "null plan");
+    if (rank) *rank = p->hp.shard_rank;
+    if (world) *world = p->hp.shard_world;
+    if (n_layouts) *n_layouts = int32_t(p->hp.layouts.size());
+    if (n_segments) *n_segments = int32_t(p->hp.segments.size());
+    if (max_local_rows) *max_local_rows = p->hp.max_local_rows;
+    return 0;
+}
+
+int tcc_shard_segment(const tcc_plan* p, int seg, int32_t* layout, int32_t* batch_lo, int32_t* batch_hi) {
+    if (!p || seg < 0 || seg >= int(p->hp.segments.size())) return fail(TCC_ERR_BAD_ARGUMENT, "segment index out of range");
+    const Segment& s = p->hp.segments[seg];
+    if (layout) *layout = s.layout;
+    if (batch_lo) *batch_lo = s.batch_lo;
+    if (batch_hi) *batch_hi = s.batch_hi;
+    return 0;
+}
+
+int tcc_shard_layout(const tcc_plan* p, int layout, int32_t* owner_host /* [num_strings], storage order */,
+                     uint32_t* orbital_mask) {
+    if (!p || layout < 0 || layout >= int(p->hp.layouts.size())) return fail(TCC_ERR_BAD_ARGUMENT, "layout index out of range");
+    const RowLayout& L = p->hp.layouts[layout];
+    if (owner_host)
+        for (int64_t a = 0; a < p->hp.nstr; ++a) owner_host[a] = L.owner[a];
+    if (orbital_mask) *orbital_mask = L.T;
+    return 0;
+}
+
+int tcc_shard_set_params(tcc_plan* p, const double* params_host, void* stream) {
+    if (!p || (!params_host && p->hp.n_params > 0)) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc = prepare_rot(p, params_host, cudaStream_t(stream))) return rc;
+    CUDA_TRY(cudaMemsetAsync(p->grad_ops, 0, sizeof(double) * (p->hp.ops.size() + 8), cudaStream_t(stream)));
+    return 0;
+}
+
+int tcc_shard_forward(tcc_plan* p, int seg, double* vec_local_dev, void* stream) {
+    if (!p || !vec_local_dev || seg < 0 || seg >= int(p->hp.segments.size())) return fail(TCC_ERR_BAD_ARGUMENT, "bad argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    cudaStream_t st = cudaStream_t(stream);
+    const Segment& s = p->hp.segments[seg];
+    p->prof.mark(TCC_PROF_FWD_BATCH, st);
+    for (int b = s.batch_lo; b < s.batch_hi; ++b) {
+        BatchDevSet& db = p->dbatches[b];
+        launch_batch_forward(vec_local_dev, p->hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st,
+                             &p->fan);
+        p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
+        p->launches += 1;
+    }
+    p->prof.mark(-1, st);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int tcc_shard_reverse(tcc_plan* p, int seg, double* ket_local_dev, double* bra_local_dev, void* stream) {
+    if (!p || !ket_local_dev || !bra_local_dev || seg < 0 || seg >= int(p->hp.segments.size()))
+        return fail(TCC_ERR_BAD_ARGUMENT, "bad argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    cudaStream_t st = cudaStream_t(stream);
+    const Segment& s = p->hp.segments[seg];
+    p->prof.mark(TCC_PROF_REV_BATCH, st);
+    for (int b = s.batch_hi - 1; b >= s.batch_lo; --b) {
+        BatchDevSet& db = p->dbatches[b];
+        launch_batch_reverse(ket_local_dev, bra_local_dev, p->hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart,
+                             p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
+        p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
+        p->launches += 2;
+    }
+    p->prof.mark(-1, st);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// this rank's share of the gradient (sum over its tiles), by parameter, with the factor 2 of evolve_civector.py:218;
+// the caller adds the shares of all ranks
+int tcc_shard_gradient(tcc_plan* p, double* grad_host, void* stream) {
+    if (!p || !grad_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    cudaStream_t st = cudaStream_t(stream);
+    const HostPlan& hp = p->hp;
+    const int m = int(hp.ops.size());
+    CUDA_TRY(cudaMemcpyAsync(p->pinned, p->grad_ops, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    p->prof.resolve();
+    for (int i = 0; i < hp.n_params; ++i) grad_host[i] = 0.0;
+    for (int j = 0; j < m; ++j) grad_host[hp.ops[j].param] += p->pinned[j];
+    for (int i = 0; i < hp.n_params; ++i) grad_host[i] *= 2.0;
+    return 0;
+}
+
+// Contributions to sigma = H c of the storage rows [row_lo, row_lo + row_cnt): the same-spin terms OF these rows and
+// the opposite-spin terms scattered FROM these rows, ADDED into sigma_full_dev (the caller zeroes it).  c_full_dev and
+// sigma_full_dev are full [na, nb] storage-order matrices; the sum over a partition of the rows is H c.
+int tcc_apply_h_rows(tcc_plan* p, const double* c_full_dev, double* sigma_full_dev, int64_t row_lo, int64_t row_cnt, void* stream) {
+    if (!p || !c_full_dev || !sigma_full_dev) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    HostPlan& hp = p->hp;
+    if (hp.hcb) return fail(TCC_ERR_BAD_ARGUMENT, "hcb plans have a single row");
+    if (!p->has_h) return fail(TCC_ERR_NO_HAMILTONIAN, "tcc_set_hamiltonian has not been called");
+    if (row_lo < 0 || row_cnt < 0 || row_lo + row_cnt > hp.na) return fail(TCC_ERR_BAD_ARGUMENT, "row range out of bounds");
+    if (row_cnt == 0) return 0;
+    cudaStream_t st = cudaStream_t(stream);
+    const size_t need = size_t(row_cnt) * size_t(hp.nb);
+    if (p->rows_ws_cap < need) {
+        cudaFree(p->rows_ws1);
+        cudaFree(p->rows_ws2);
+        p->rows_ws1 = p->rows_ws2 = nullptr;
+        p->rows_ws_cap = 0;
+        CUDA_TRY(dev_alloc(p, &p->rows_ws1, need));
+        CUDA_TRY(dev_alloc(p, &p->rows_ws2, need));
+        p->rows_ws_cap = need;
+    }
+    const double* c_rows = c_full_dev + row_lo * hp.nb;
+    double* s_rows = sigma_full_dev + row_lo * hp.nb;
+    p->prof.mark(TCC_PROF_SIGMA_SS, st);
+    // alpha-alpha: output rows of the range gather from all rows of c
+    launch_spmm_rows(c_full_dev, s_rows, row_cnt, hp.nb, p->d_ell_col + row_lo * hp.ell_width, p->d_ell_val + row_lo * hp.ell_width,
+                     hp.ell_width, true, 1, st);
+    // beta-beta acts inside each row: transpose the row block, contract, transpose back
+    launch_transpose(c_rows, p->rows_ws1, row_cnt, hp.nb, false, 1, st);
+    launch_spmm_rows(p->rows_ws1, p->rows_ws2, hp.nb, row_cnt, p->d_ell_col, p->d_ell_val, hp.ell_width, false, 1, st);
+    launch_transpose(p->rows_ws2, s_rows, hp.nb, row_cnt, true, 1, st);
+    p->prof.count(TCC_PROF_SIGMA_SS, 4, 9 * 8 * int64_t(need));
+    p->prof.mark(TCC_PROF_SIGMA_AB, st);
+    launch_sigma_ab(c_full_dev, sigma_full_dev, hp.na, hp.nb, p->d_links, hp.ml, p->d_w, hp.n, p->n2p, p->d_kmap, 1, st, row_lo, row_cnt);
+    p->prof.count(TCC_PROF_SIGMA_AB, (row_cnt + 65534) / 65535, 3 * 8 * int64_t(need));
+    p->prof.mark(-1, st);
+    p->launches += 4 + (row_cnt + 65534) / 65535;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+
 int tcc_profile_batches(tcc_plan* p, int on, float* fwd_ms, float* rev_ms) {
     if (!p) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
@@ -1092,6 +1268,7 @@ int tcc_profile_read(tcc_plan* p, double* ms, int64_t* launches, int64_t* bytes)
 int tcc_civector_host(tcc_plan* p, const double* params_host, const double* init_host, double* out_host) {
     if (!p || !out_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
     if (int rc = ensure_vec(p, &p->io1)) return rc;
     if (int rc = ensure_vec(p, &p->io2)) return rc;
     const size_t bytes = p->hp.N * sizeof(double);
@@ -1119,6 +1296,7 @@ int tcc_energy_and_grad_host(tcc_plan* p, const double* params_host, const doubl
                              double* grad_host) {
     if (!p || !energy_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
     const double* init_dev = nullptr;
     if (init_host) {
         if (int rc = ensure_vec(p, &p->io1)) return rc;

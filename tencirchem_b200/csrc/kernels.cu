@@ -447,7 +447,7 @@ __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict
 }
 
 void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, const Link* links, int ml, const double* w,
-                     int n, int n2p, const uint16_t* kmap, int n_sets, cudaStream_t st) {
+                     int n, int n2p, const uint16_t* kmap, int n_sets, cudaStream_t st, int64_t row_lo, int64_t row_cnt) {
     int units = (ml / 8) * (SAB_T / 16);
     int best_nw = 4;
     double best_eff = 0.0;
@@ -465,10 +465,11 @@ void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, con
         cudaFuncSetAttribute(sigma_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         configured = smem;
     }
-    int64_t gy_total = na;
+    // source rows [row_lo, row_lo + row_cnt) (default: all); their contributions go to every linked row of sigma
+    const int64_t r_begin = row_cnt < 0 ? 0 : row_lo, gy_total = row_cnt < 0 ? na : row_lo + row_cnt;
     unsigned gx = unsigned((nb + SAB_T - 1) / SAB_T);
     // grid.y is limited to 65535: launch in row batches
-    for (int64_t r0 = 0; r0 < gy_total; r0 += 65535) {
+    for (int64_t r0 = r_begin; r0 < gy_total; r0 += 65535) {
         unsigned gy = unsigned(gy_total - r0 < 65535 ? gy_total - r0 : 65535);
         sigma_ab_kernel<<<dim3(gx, gy, unsigned(n_sets)), best_nw * 32, smem, st>>>(c, sigma, nb, links, ml, w, n, n2p, r0, na * nb, kmap);
     }

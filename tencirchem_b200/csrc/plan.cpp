@@ -255,7 +255,9 @@ std::vector<std::vector<int>> HostPlan::group_ops(int tile_elems) const {
                 uint32_t nsa = sa | oa, nsb = sb | ob;
                 int64_t ca = max_class(hcb ? 0 : popc(nsa)), cb = max_class(popc(nsb));
                 // keep tiles roughly square: a long thin tile has row segments too short to coalesce
-                if ((ca * cb <= tile_elems && ca <= side_cap && cb <= side_cap) || batch.empty()) {
+                // sharded plans: log2(world) alpha orbitals must stay inactive, they carry the row layout of the batch
+                const bool rows_ok = shard_world == 1 || popc(nsa) + shard_bits() <= n;
+                if ((ca * cb <= tile_elems && ca <= side_cap && cb <= side_cap && rows_ok) || batch.empty()) {
                     batch.push_back(j);
                     sa = nsa;
                     sb = nsb;
@@ -315,7 +317,8 @@ void HostPlan::build_strings() {
     }
 }
 
-void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string, bool pack_classes) {
+void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string, bool pack_classes,
+                          const RowLayout* rows) {
     side->S = S;
     side->m = popc(S);
     const int m = side->m;
@@ -326,6 +329,8 @@ void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool si
     std::vector<uint32_t> cls_sigma;
     std::vector<int> cls_e;
     for (int64_t a = 0; a < count; ++a) {
+        // sharded alpha side: only the rows of this rank, addressed by their local row
+        if (rows && rows->owner[a] != shard_rank) continue;
         uint32_t s = single_string ? 0u : strings[a];
         uint32_t sig = s & ~S;
         auto it = cls_of.find(sig);
@@ -339,7 +344,7 @@ void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool si
         } else {
             id = it->second;
         }
-        members[id].push_back(uint32_t(a));
+        members[id].push_back(rows ? rows->local_row[a] : uint32_t(a));
     }
     side->addr.clear();
     side->ord.clear();
@@ -413,7 +418,7 @@ static uint32_t compress_bits(uint32_t bits, const std::vector<int>& act) {
     return t;
 }
 
-void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch* out) {
+void HostPlan::active_sets(const std::vector<int>& group, int tile_elems, uint32_t* sa_out, uint32_t* sb_out) const {
     uint32_t sa = 0, sb = 0;
     for (int j : group) {
         sa |= ops[j].cre_a | ops[j].ann_a;
@@ -434,6 +439,8 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
                 if (!beta && (hcb || sa == 0)) continue;  // a side without hops stays unexpanded
                 if (beta && sb == 0) continue;
                 uint32_t& s = beta ? sb : sa;
+                // a sharded plan keeps log2(world) alpha orbitals out of every active set: they carry the row layout
+                if (!beta && shard_world > 1 && popc(sa) + shard_bits() >= n) continue;
                 for (int o : by_pos) {
                     if (s >> o & 1) continue;
                     uint32_t ns = s | (1u << o);
@@ -448,6 +455,12 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
             }
         }
     }
+    *sa_out = sa;
+    *sb_out = sb;
+}
+
+void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch* out) {
+    const uint32_t sa = out->sa, sb = out->sb;  // set by finalize (active_sets)
     int64_t ca = max_class(hcb ? 0 : popc(sa)), cb = max_class(popc(sb));
     int64_t pa = ca, pb = cb;
     // spend the remaining capacity: first make the contiguous (beta) direction at least 128 wide, then rows
@@ -464,8 +477,8 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
     // class packing needs hops on both sides (a side without active orbitals takes the repeat path of the kernel)
     const bool pack = popc(sb) > 0 && (hcb || popc(sa) > 0) &&
                       (std::getenv("TCC_B200_PACK") ? std::atoi(std::getenv("TCC_B200_PACK")) != 0 : true);
-    build_side(sa, int(pa), &out->A, hcb != 0, pack);
-    build_side(sb, int(pb), &out->B, false, pack);
+    build_side(sa, int(pa), &out->A, hcb != 0, pack, shard_world > 1 ? &layouts[out->layout] : nullptr);
+    build_side(sb, int(pb), &out->B, false, pack, nullptr);
     auto make_tables = [&](SideBatch& side) {
         const int m = side.m;
         std::vector<int> act;  // active orbitals sorted by storage bit position
@@ -615,14 +628,90 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
     if (out->plist.empty()) out->plist.push_back(0);
 }
 
-void HostPlan::finalize(int tile_elems, bool use_layout) {
+// Row layouts of a sharded plan.  A batch can run in a layout whose orbitals T are not active on its alpha side.
+// The layout is kept while it fits; when a batch needs a change, the new T takes the admissible orbitals whose
+// next alpha activity lies farthest ahead (the UCCSD generator order sweeps the occupied index slowly, so a
+// whole sweep needs a handful of layouts).
+void HostPlan::choose_row_layouts() {
+    layouts.clear();
+    segments.clear();
+    int t = 0;
+    while ((1 << t) < shard_world) ++t;
+    const int nb_ = int(batches.size());
+    auto make_layout = [&](uint32_t T) {
+        RowLayout L;
+        L.T = T;
+        L.owner.assign(nstr, 0);
+        L.local_row.assign(nstr, 0);
+        L.rows.assign(shard_world, 0);
+        std::vector<int> torb;
+        for (int o = 0; o < n; ++o)
+            if (T >> o & 1) torb.push_back(o);
+        for (int64_t a = 0; a < nstr; ++a) {
+            int pat = 0;
+            for (size_t i = 0; i < torb.size(); ++i)
+                if (strings[a] >> torb[i] & 1) pat |= 1 << i;
+            L.owner[a] = uint8_t(pat);
+            L.local_row[a] = uint32_t(L.rows[pat]++);
+        }
+        return L;
+    };
+    if (shard_world == 1 || hcb) {
+        layouts.push_back(make_layout(0));
+        for (auto& b : batches) b.layout = 0;
+        if (nb_) segments.push_back(Segment{0, 0, nb_});
+        max_local_rows = hcb ? 1 : nstr;
+        return;
+    }
+    // next_use[b][o]: first batch >= b whose alpha active set holds orbital o
+    std::vector<std::vector<int>> next_use(nb_ + 1, std::vector<int>(n, nb_));
+    for (int b = nb_ - 1; b >= 0; --b)
+        for (int o = 0; o < n; ++o) next_use[b][o] = (batches[b].sa >> o & 1) ? b : next_use[b + 1][o];
+    std::map<uint32_t, int> layout_of;
+    uint32_t cur = 0;
+    bool have = false;
+    for (int b = 0; b < nb_; ++b) {
+        if (!have || (cur & batches[b].sa)) {
+            std::vector<int> cand;
+            for (int o = 0; o < n; ++o)
+                if (!(batches[b].sa >> o & 1)) cand.push_back(o);
+            std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) { return next_use[b][x] > next_use[b][y]; });
+            cur = 0;
+            for (int i = 0; i < t && i < int(cand.size()); ++i) cur |= 1u << cand[i];
+            have = true;
+        }
+        auto it = layout_of.find(cur);
+        if (it == layout_of.end()) {
+            it = layout_of.emplace(cur, int(layouts.size())).first;
+            layouts.push_back(make_layout(cur));
+        }
+        batches[b].layout = it->second;
+        if (segments.empty() || segments.back().layout != it->second)
+            segments.push_back(Segment{it->second, b, b + 1});
+        else
+            segments.back().batch_hi = b + 1;
+    }
+    if (layouts.empty()) layouts.push_back(make_layout(t ? (1u << t) - 1 : 0));
+    max_local_rows = 0;
+    for (const auto& L : layouts) max_local_rows = std::max(max_local_rows, L.rows[shard_rank]);
+}
+
+void HostPlan::finalize(int tile_elems, bool use_layout, int rank, int world) {
     tile_elems = std::max(tile_elems, 64);
+    shard_rank = rank;
+    shard_world = world;
+    if (world > 1 && shard_bits() + 2 > n) {
+        error = "too many ranks for this active space: log2(world) + 2 alpha orbitals are needed";
+        return;
+    }
     std::vector<std::vector<int>> groups = group_ops(tile_elems);
     choose_layout(groups, use_layout);
     build_strings();
     for (auto& op : ops) attach_hops(&op);
     batches.clear();
     batches.resize(groups.size());
+    for (size_t g = 0; g < groups.size(); ++g) active_sets(groups[g], tile_elems, &batches[g].sa, &batches[g].sb);
+    choose_row_layouts();
     for (size_t g = 0; g < groups.size(); ++g) build_batch(groups[g], tile_elems, &batches[g]);
 }
 

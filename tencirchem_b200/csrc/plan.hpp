@@ -99,6 +99,22 @@ struct Batch {
     std::vector<uint32_t> plist;
     std::vector<int32_t> plist_index;  // [n_ops][m_a + 1][m_b + 1][2] = (offset, count)
     int ld_fixed = 0;                  // tile leading dimension when the beta side has no active orbitals
+    uint32_t sa = 0, sb = 0;           // padded active sets
+    int layout = 0;                    // row distribution the batch runs in (sharded plans)
+};
+
+// Row distribution of a sharded plan: alpha string a lives on rank owner[a] (the occupation pattern of the
+// orbitals T, none of which is active on the alpha side of the batches that use the layout, so every alpha class
+// lies on one rank) at local row local_row[a] (ascending storage address within the rank).
+struct RowLayout {
+    uint32_t T = 0;
+    std::vector<uint8_t> owner;       // [nstr]
+    std::vector<uint32_t> local_row;  // [nstr]
+    std::vector<int64_t> rows;        // [world] rows per rank
+};
+
+struct Segment {  // run of consecutive batches with the same layout
+    int layout, batch_lo, batch_hi;
 };
 
 struct HostPlan {
@@ -117,6 +133,16 @@ struct HostPlan {
     std::map<uint64_t, int> hop_index;
     std::vector<OpDesc> ops;
     std::vector<Batch> batches;
+    // alpha-row sharding (world == 1: one layout that owns everything)
+    int shard_rank = 0, shard_world = 1;
+    std::vector<RowLayout> layouts;
+    std::vector<Segment> segments;
+    int64_t max_local_rows = 0;  // over the layouts, for this rank
+    int shard_bits() const {
+        int t = 0;
+        while ((1 << t) < shard_world) ++t;
+        return t;
+    }
     int n_params = 0;
     std::string error;
 
@@ -125,7 +151,7 @@ struct HostPlan {
     int parse_op(const int32_t* idx, int len, int param, OpDesc* op);
     // groups ops into batches (orbital sets only), picks the storage order, builds strings, hop tables
     // and batch descriptors.  tile_elems = max determinants per on-chip tile.
-    void finalize(int tile_elems, bool use_layout);
+    void finalize(int tile_elems, bool use_layout, int rank = 0, int world = 1);
     void attach_hops(OpDesc* op);
 
     uint32_t permute_bits(uint32_t s) const;
@@ -152,8 +178,11 @@ struct HostPlan {
     std::vector<std::vector<int>> group_ops(int tile_elems) const;
     void choose_layout(const std::vector<std::vector<int>>& groups, bool use_layout);
     void build_strings();
+    void active_sets(const std::vector<int>& group, int tile_elems, uint32_t* sa, uint32_t* sb) const;
+    void choose_row_layouts();
     void build_batch(const std::vector<int>& group, int tile_elems, Batch* out);
-    void build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string, bool pack_classes);
+    void build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string, bool pack_classes,
+                    const RowLayout* rows);
     int64_t max_class(int m) const;
 };
 

@@ -24,8 +24,9 @@ def _dptr(a: Optional[np.ndarray]):
 
 class Plan:
     def __init__(self, n_qubits: int, n_elec: int, ex_ops: Sequence[Sequence[int]], param_ids=None,
-                 hcb: bool = False, device: Optional[int] = 0):
-        """``device=None`` builds a host-only plan (strings / table introspection, no compute)."""
+                 hcb: bool = False, device: Optional[int] = 0, shard: Optional[Sequence[int]] = None):
+        """``device=None`` builds a host-only plan (strings / table introspection, no compute).
+        ``shard=(rank, world)`` builds the plan of one rank of an alpha-row sharded engine (tcc_plan_create_sharded)."""
         self.lib = _lib.load()
         self.n_qubits, self.n_elec, self.hcb = int(n_qubits), int(n_elec), bool(hcb)
         self.ex_ops = tuple(tuple(int(i) for i in op) for op in ex_ops)
@@ -39,13 +40,24 @@ class Plan:
         pids = np.asarray(self.param_ids, dtype=np.int32)
         handle = C.c_void_p()
         ip = C.POINTER(C.c_int32)
-        _lib.check(
-            self.lib.tcc_plan_create(
-                self.n_qubits, self.n_elec, int(self.hcb), len(self.ex_ops),
-                flat.ctypes.data_as(ip), lens.ctypes.data_as(ip), pids.ctypes.data_as(ip),
-                -1 if device is None else int(device), C.byref(handle),
+        if shard is None:
+            _lib.check(
+                self.lib.tcc_plan_create(
+                    self.n_qubits, self.n_elec, int(self.hcb), len(self.ex_ops),
+                    flat.ctypes.data_as(ip), lens.ctypes.data_as(ip), pids.ctypes.data_as(ip),
+                    -1 if device is None else int(device), C.byref(handle),
+                )
             )
-        )
+        else:
+            if self.hcb:
+                raise ValueError("hcb plans have a single alpha row and are not sharded")
+            _lib.check(
+                self.lib.tcc_plan_create_sharded(
+                    self.n_qubits, self.n_elec, len(self.ex_ops),
+                    flat.ctypes.data_as(ip), lens.ctypes.data_as(ip), pids.ctypes.data_as(ip),
+                    -1 if device is None else int(device), int(shard[0]), int(shard[1]), C.byref(handle),
+                )
+            )
         self.handle = handle
         self.device = device
         self.size = int(self.lib.tcc_civector_size(handle))
@@ -96,6 +108,60 @@ class Plan:
         info = {k: v.value for k, v in zip(keys, vals)}
         info["op_indices"] = idx[:n_ops].tolist()
         return info
+
+    # ---- alpha-row sharding (include/tcc_b200.h, multi-GPU section) ----
+    def shard_info(self) -> dict:
+        v = [C.c_int32(0) for _ in range(4)]
+        rows = C.c_int64(0)
+        _lib.check(self.lib.tcc_shard_info(self.handle, *[C.byref(x) for x in v], C.byref(rows)))
+        return dict(rank=v[0].value, world=v[1].value, n_layouts=v[2].value, n_segments=v[3].value,
+                    max_local_rows=rows.value)
+
+    def shard_segments(self) -> list:
+        """[(layout, batch_lo, batch_hi)] in application order."""
+        out = []
+        for seg in range(self.shard_info()["n_segments"]):
+            v = [C.c_int32(0) for _ in range(3)]
+            _lib.check(self.lib.tcc_shard_segment(self.handle, seg, *[C.byref(x) for x in v]))
+            out.append(tuple(x.value for x in v))
+        return out
+
+    def shard_layout(self, layout: int):
+        """(owner[num_strings] of every storage row, orbital mask T) of a row layout."""
+        owner = np.zeros(self.n_strings, dtype=np.int32)
+        mask = C.c_uint32(0)
+        _lib.check(self.lib.tcc_shard_layout(self.handle, int(layout), owner.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(mask)))
+        return owner, mask.value
+
+    def shard_set_params(self, params):
+        params = _f64(params)
+        if params.shape != (self.n_params,):
+            raise ValueError(f"Incompatible parameter shape. {(self.n_params,)} is desired. Got {params.shape}")
+        _lib.check(self.lib.tcc_shard_set_params(self.handle, _dptr(params), self._stream()))
+
+    def shard_forward(self, seg: int, vec_local):
+        _lib.check(self.lib.tcc_shard_forward(self.handle, int(seg), C.c_void_p(vec_local.data_ptr()), self._stream()))
+
+    def shard_reverse(self, seg: int, ket_local, bra_local):
+        _lib.check(self.lib.tcc_shard_reverse(self.handle, int(seg), C.c_void_p(ket_local.data_ptr()),
+                                              C.c_void_p(bra_local.data_ptr()), self._stream()))
+
+    def shard_gradient(self) -> np.ndarray:
+        g = np.zeros(max(self.n_params, 1), dtype=np.float64)
+        _lib.check(self.lib.tcc_shard_gradient(self.handle, _dptr(g), self._stream()))
+        return g[: self.n_params]
+
+    def apply_h_rows(self, c_full, sigma_full, row_lo: int, row_cnt: int):
+        """sigma_full += contributions of storage rows [row_lo, row_lo + row_cnt) to H c (full storage-order matrices)."""
+        _lib.check(self.lib.tcc_apply_h_rows(self.handle, C.c_void_p(c_full.data_ptr()), C.c_void_p(sigma_full.data_ptr()),
+                                             int(row_lo), int(row_cnt), self._stream()))
+
+    def to_storage_order_dev(self, ref, out):
+        """out (storage order) <- ref (reference order); full CI vectors on the device."""
+        _lib.check(self.lib.tcc_to_storage_order(self.handle, self._ptr(ref), self._ptr(out), self._stream()))
+
+    def from_storage_order_dev(self, storage, out):
+        _lib.check(self.lib.tcc_from_storage_order(self.handle, self._ptr(storage), self._ptr(out), self._stream()))
 
     def storage_order(self) -> np.ndarray:
         """ref2int: storage address of each per-spin string, indexed by its reference address."""

@@ -1,0 +1,256 @@
+"""Alpha-row sharded UCC engine: one CI vector spread over `world` GPUs (the large-N regime).
+
+Every rank holds the rows of the [na, nb] CI matrix whose occupation pattern on t = log2(world) alpha orbitals T
+equals its rank.  T is chosen per batch among the orbitals that are not active on the alpha side of the batch
+(include/tcc_b200.h, multi-GPU section), so all batch kernels run on local rows; only when T changes do rows move
+between ranks (one all-to-all per vector).  H c works on row blocks of the gathered vector (`tcc_apply_h_rows`) and
+is summed with an all-reduce, which needs the full vector on every GPU: fine up to (18e,18o) (18.9 GB); the
+(20e,20o) vector needs the three-layout sigma of DESIGN.md section 6 instead (not built).
+
+The same driver runs
+* one rank per process over `torch.distributed` (NCCL; `TorchComm`), and
+* all ranks inside one process on one GPU (`LocalComm`): the parity tests exercise every layout change, ownership
+  map and partial-gradient sum without needing a multi-GPU box.
+
+Mirrors get_energy_and_grad_civector / get_civector (tencirchem/static/evolve_civector.py:180-218).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+
+from .plan import Plan
+from .parallel import shard_bounds
+
+
+class LocalComm:
+    """All ranks live in this process (virtual ranks on one device): collectives are local copies."""
+
+    def __init__(self, world: int):
+        self.world = int(world)
+        self.local_ranks = list(range(self.world))
+
+    def exchange(self, send: List[List["torch.Tensor"]]) -> List[List["torch.Tensor"]]:
+        # send[i][d]: rows that local rank i sends to rank d  ->  recv[i][s]: rows rank i receives from rank s
+        return [[send[s][d] for s in range(self.world)] for d in range(self.world)]
+
+    def all_reduce_sum(self, tensors: List["torch.Tensor"]):
+        total = tensors[0].clone()
+        for t in tensors[1:]:
+            total += t
+        for t in tensors:
+            t.copy_(total)
+
+
+class TorchComm:
+    """One rank per process over torch.distributed (NCCL on GPUs; gloo in the CPU tests)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.local_ranks = [self.rank]
+
+    def exchange(self, send):
+        import torch
+
+        (mine,) = send
+        recv = [torch.empty(0)] * self.world
+        ops = []
+        counts = torch.tensor([t.shape[0] for t in mine], dtype=torch.int64, device=mine[self.rank].device)
+        all_counts = [torch.empty_like(counts) for _ in range(self.world)]
+        self.dist.all_gather(all_counts, counts)
+        for peer in range(self.world):
+            if peer == self.rank:
+                recv[peer] = mine[peer]
+                continue
+            n_in = int(all_counts[peer][self.rank])
+            recv[peer] = torch.empty((n_in,) + tuple(mine[peer].shape[1:]), dtype=mine[peer].dtype, device=mine[peer].device)
+            if mine[peer].numel():
+                ops.append(self.dist.P2POp(self.dist.isend, mine[peer].contiguous(), peer))
+            if n_in:
+                ops.append(self.dist.P2POp(self.dist.irecv, recv[peer], peer))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+        return [recv]
+
+    def all_reduce_sum(self, tensors):
+        (t,) = tensors
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+
+
+class RowMover:
+    """Moves the rows of local [rows, nb] matrices between the row layouts of a sharded plan.  Host logic only
+    (index maps from `tcc_shard_layout`); the tensors may live on the GPU (NCCL) or on the CPU (gloo tests)."""
+
+    def __init__(self, plan: Plan, comm, device):
+        import torch
+
+        self.torch = torch
+        self.comm = comm
+        self.world = comm.world
+        self.device = device
+        self.nb = plan.n_strings
+        info = plan.shard_info()
+        self.owner = [plan.shard_layout(l)[0] for l in range(info["n_layouts"])]
+        # rows[l][r]: storage rows of rank r in layout l, ascending (= its local row order)
+        self.rows = [[np.nonzero(own == r)[0] for r in range(self.world)] for own in self.owner]
+        self._moves = {}
+        self.reshards = 0
+
+    def _move_plan(self, l_from: int, l_to: int, rank: int):
+        key = (l_from, l_to, rank)
+        if key not in self._moves:
+            t = self.torch
+            mine_from = self.rows[l_from][rank]
+            mine_to = self.rows[l_to][rank]
+            send_idx, recv_idx = [], []
+            for peer in range(self.world):
+                out_rows = np.intersect1d(mine_from, self.rows[l_to][peer], assume_unique=True)
+                in_rows = np.intersect1d(self.rows[l_from][peer], mine_to, assume_unique=True)
+                send_idx.append(t.as_tensor(np.searchsorted(mine_from, out_rows), dtype=t.int64, device=self.device))
+                recv_idx.append(t.as_tensor(np.searchsorted(mine_to, in_rows), dtype=t.int64, device=self.device))
+            self._moves[key] = (send_idx, recv_idx, len(mine_to))
+        return self._moves[key]
+
+    def reshard(self, vecs: List["torch.Tensor"], l_from: int, l_to: int) -> List["torch.Tensor"]:
+        """vecs[i]: local [rows, nb] matrix of the i-th local rank in layout l_from -> the same in layout l_to."""
+        t = self.torch
+        if l_from == l_to:
+            return vecs
+        self.reshards += 1
+        plans = [self._move_plan(l_from, l_to, r) for r in self.comm.local_ranks]
+        send = [[v.index_select(0, idx) for idx in mp[0]] for v, mp in zip(vecs, plans)]
+        recv = self.comm.exchange(send)
+        out = []
+        for v, mp, got in zip(vecs, plans, recv):
+            new = t.empty((mp[2],) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device)
+            for idx, rows in zip(mp[1], got):
+                if idx.numel():
+                    new.index_copy_(0, idx, rows)
+            out.append(new)
+        return out
+
+
+class _RankState:
+    def __init__(self, plan: Plan, rank: int):
+        self.plan = plan
+        self.rank = rank
+
+
+class ShardedUCC:
+    """energy / energy_and_grad / civector of one ansatz with the CI vector sharded over `comm.world` ranks."""
+
+    def __init__(self, n_qubits, n_elec, ex_ops, param_ids, comm, device=0):
+        import torch
+
+        self.torch = torch
+        self.comm = comm
+        self.world = comm.world
+        self.device = torch.device("cuda", int(device))
+        self.states = [_RankState(Plan(n_qubits, n_elec, ex_ops, param_ids, device=int(device), shard=(r, self.world)), r)
+                       for r in comm.local_ranks]
+        p0 = self.states[0].plan
+        self.n_params, self.na = p0.n_params, p0.n_strings
+        self.nb = p0.n_strings
+        self.segments = p0.shard_segments()
+        self.mover = RowMover(p0, comm, self.device)
+        self.rows = self.mover.rows
+        self.hf_row = int(p0.storage_order()[0])  # HF determinant = reference address 0 of both spins
+
+    @property
+    def reshards(self) -> int:
+        return self.mover.reshards
+
+    def set_hamiltonian(self, int1e, int2e):
+        for st in self.states:
+            st.plan.set_hamiltonian(int1e, int2e)
+
+    def _reshard(self, vecs, l_from, l_to):
+        return self.mover.reshard(vecs, l_from, l_to)
+
+    # ---- the path -----------------------------------------------------------------------------------
+    def _forward(self, params):
+        t = self.torch
+        first = self.segments[0][0] if self.segments else 0
+        kets = []
+        for st in self.states:
+            st.plan.shard_set_params(params)
+            rows = self.rows[first][st.rank]
+            ket = t.zeros((len(rows), self.nb), dtype=t.float64, device=self.device)
+            pos = np.searchsorted(rows, self.hf_row)
+            if pos < len(rows) and rows[pos] == self.hf_row:
+                ket[pos, self.hf_row] = 1.0
+            kets.append(ket)
+        layout = first
+        for seg, (l, _, _) in enumerate(self.segments):
+            kets = self._reshard(kets, layout, l)
+            layout = l
+            for st, ket in zip(self.states, kets):
+                if ket.numel():  # a rank may own no row in a layout of a tiny active space
+                    st.plan.shard_forward(seg, ket)
+        return kets, layout
+
+    def _gather_full(self, vecs, layout):
+        """Full [na, nb] storage-order matrix on every rank (zero-padded own rows, summed)."""
+        t = self.torch
+        fulls = []
+        for st, v in zip(self.states, vecs):
+            full = t.zeros((self.na, self.nb), dtype=t.float64, device=self.device)
+            full[t.as_tensor(self.rows[layout][st.rank], dtype=t.int64, device=self.device)] = v
+            fulls.append(full)
+        self.comm.all_reduce_sum(fulls)
+        return fulls
+
+    def civector(self, params) -> np.ndarray:
+        """Reference-order CI vector on the host (small systems / tests: gathers the full vector)."""
+        t = self.torch
+        kets, layout = self._forward(np.asarray(params, dtype=np.float64))
+        full = self._gather_full(kets, layout)[0].reshape(-1)
+        out = t.empty_like(full)
+        self.states[0].plan.from_storage_order_dev(full, out)
+        t.cuda.synchronize()
+        return out.cpu().numpy()
+
+    def energy_and_grad(self, params, want_grad: bool = True):
+        t = self.torch
+        params = np.asarray(params, dtype=np.float64)
+        kets, layout = self._forward(params)
+        # sigma = H c: every rank contracts a block of rows of the gathered vector; the blocks are summed
+        c_full = self._gather_full(kets, layout)
+        s_full = []
+        for st, c in zip(self.states, c_full):
+            sig = t.zeros_like(c)
+            lo, hi = shard_bounds(self.na, st.rank, self.world)
+            st.plan.apply_h_rows(c, sig, lo, hi - lo)
+            s_full.append(sig)
+        del c_full
+        self.comm.all_reduce_sum(s_full)
+        bras, parts = [], []
+        for st, sig, ket in zip(self.states, s_full, kets):
+            bra = sig[t.as_tensor(self.rows[layout][st.rank], dtype=t.int64, device=self.device)].contiguous()
+            bras.append(bra)
+            parts.append((bra * ket).sum().reshape(1))
+        del s_full
+        self.comm.all_reduce_sum(parts)
+        energy = float(parts[0][0])
+        if not want_grad:
+            return energy, None
+        for seg in range(len(self.segments) - 1, -1, -1):
+            l = self.segments[seg][0]
+            kets = self._reshard(kets, layout, l)
+            bras = self._reshard(bras, layout, l)
+            layout = l
+            for st, ket, bra in zip(self.states, kets, bras):
+                if ket.numel():
+                    st.plan.shard_reverse(seg, ket, bra)
+        grads = [t.as_tensor(st.plan.shard_gradient(), dtype=t.float64, device=self.device) for st in self.states]
+        self.comm.all_reduce_sum(grads)
+        return energy, grads[0].cpu().numpy()
+
+    def energy(self, params) -> float:
+        return self.energy_and_grad(params, want_grad=False)[0]

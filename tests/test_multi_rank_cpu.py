@@ -68,3 +68,56 @@ def test_shard_sizes_are_balanced():
         sizes = [b - a for a, b in bounds]
         assert max(sizes) - min(sizes) <= 1
         assert all(bounds[i][1] == bounds[i + 1][0] for i in range(w - 1))
+
+
+def _reshard_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ["TCC_B200_TILE_ELEMS"] = "400"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pools
+    from tencirchem_b200.plan import Plan
+    from tencirchem_b200.sharded import RowMover, TorchComm
+
+    ex_ops, param_ids = pools.uccsd_ex_ops(3, 3)[:2]
+    plan = Plan(12, 6, ex_ops, param_ids, device=None, shard=(rank, world))  # host-only: schedule + layouts
+    mover = RowMover(plan, TorchComm(), torch.device("cpu"))
+    na = plan.n_strings
+    full = torch.arange(na * na, dtype=torch.float64).reshape(na, na)  # full[a, b] identifies its element
+    segs = plan.shard_segments()
+    layout = segs[0][0]
+    local = [full[torch.as_tensor(mover.rows[layout][rank])].clone()]
+    ok = True
+    # walk the forward sweep's layout sequence and back: after every move the rank must hold exactly its rows
+    for l in [s[0] for s in segs] + [s[0] for s in reversed(segs)]:
+        local = mover.reshard(local, layout, l)
+        layout = l
+        ok = ok and torch.equal(local[0], full[torch.as_tensor(mover.rows[l][rank])])
+    # ownership is a partition of the rows in every layout
+    for own in mover.owner:
+        ok = ok and own.min() >= 0 and own.max() < world and len(own) == na
+    covered = sorted(b for s in segs for b in range(s[1], s[2]))
+    ok = ok and covered == list(range(plan.n_batches))
+    t = torch.tensor([1.0 if ok else 0.0, float(mover.reshards)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put((t[0].item(), t[1].item(), len(segs)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_alpha_row_reshard_world2():
+    """Alpha-row sharding, host side: the rows move between the layouts of consecutive segments through
+    isend/irecv (gloo here, NCCL on GPUs) and every rank always holds exactly the rows its layout assigns."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reshard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, reshards, n_segs = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok == 1.0
+    assert n_segs > 2 and reshards >= n_segs - 1

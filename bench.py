@@ -230,6 +230,9 @@ def run_b200(args):
     m, p_count = len(ucc.ex_ops), ucc.n_params
     size = ucc.civector_size
 
+    if world > 1 and args.multi == "sharded" and not ucc.hcb and args.batch == 0:
+        return run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n)
+
     t0 = time.perf_counter()
     plan = get_plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb, device=local_rank)
     _bind_hamiltonian(plan, ucc.hamiltonian)
@@ -345,6 +348,102 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
+    """N > 1: ONE evaluation at a time, the CI vector split by alpha rows over the ranks (strong scaling;
+    tencirchem_b200/sharded.py).  Every rank evaluates the same theta; device time = MAX over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from tencirchem_b200.evolve_civector import clear_cache
+    from tencirchem_b200.sharded import ShardedUCC, TorchComm
+
+    clear_cache()
+    torch.cuda.empty_cache()
+    m, p_count, size = len(ucc.ex_ops), ucc.n_params, ucc.civector_size
+    t0 = time.perf_counter()
+    eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, TorchComm(), device=local_rank)
+    eng.set_hamiltonian(int1e, int2e)
+    staging_s = time.perf_counter() - t0
+    plan = eng.states[0].plan
+
+    def theta(step):  # the same parameters on every rank, and the same as rank 0 of the single-GPU run
+        np.random.seed((2077 + step) % (2**32))
+        return np.random.rand(p_count) - 0.5
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        eng.energy_and_grad(theta(-1 - w))
+    barrier()
+    plan.profile_enable(True)
+    launches0 = plan.launch_count
+    reshards0 = eng.reshards
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    last = None
+    for k in range(args.steps):
+        # host parameters in, host (energy, gradient) out: this call IS the public API of the sharded engine
+        last = eng.energy_and_grad(theta(k))
+    ev1.record()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = plan.profile_read()
+    plan.profile_enable(False)
+    launches = plan.launch_count - launches0
+    reshards = (eng.reshards - reshards0) // max(args.steps, 1)
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    value = args.steps / (dev_ms * 1e-3)
+    peak, peak_src = measured_peak_hbm()
+    dom = max(prof, key=lambda s_: prof[s_][0])
+    d_ms, d_launch, d_bytes = prof[dom]
+    achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+    total_prof_ms = sum(v[0] for v in prof.values())
+    phases = {s_: {"ms_per_step": round(v[0] / args.steps, 3), "launches_per_step": v[1] // args.steps,
+                   "algorithmic_GBps": round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 else None,
+                   "share": round(v[0] / total_prof_ms, 4) if total_prof_ms else None} for s_, v in prof.items()}
+    line = {
+        "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_desc(n, args.ansatz, args.integrals), "n_determinants": size, "n_excitations": m,
+                   "n_params": p_count, "l2": "inputs larger than L2" if size * 8 / world > 2.5e8 else "vectors fit in L2; no flush",
+                   "multi_gpu": f"one evaluation, CI vector sharded by alpha rows over {world} ranks; {reshards} row re-shards "
+                                f"(NCCL send/recv) per evaluation in {len(eng.segments)} segments; H.c by row blocks of the "
+                                "all-reduced vector; gradient and energy all-reduced",
+                   "n_batches": plan.n_batches, "staging_s": round(staging_s, 2)},
+        "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": 8 * p_count * world,
+                "d2h_bytes_per_step": 8 * (m + 1) * world,
+                "note": "ShardedUCC.energy_and_grad(params): host params in, host (energy, gradient) out on every rank; wall clock"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "batch_kernel<2> (rank 0's share of the rows)" if dom == "rev_batch" else dom,
+                     "phase": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": None,
+                     "avg_launch_us": 1e3 * d_ms / max(d_launch, 1), "launches": d_launch,
+                     "algorithmic_bytes_per_launch": d_bytes / max(d_launch, 1)},
+        "phases_rank0": phases,
+        "clocks": clocks,
+        "energy_last_step": last[0],
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = {"note": "reported by the N=1 run (rank 0, bounded sample); not repeated at N>1"}
+    print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def run_b200_batched(args, plan, ucc, theta, barrier, world, rank, n, staging_s):
     """Small-active-space regime (BASELINE configs 1-2): B random theta per step through tcc_energy_and_grad_batch."""
     import torch
@@ -427,6 +526,9 @@ def main():
                     help="random_integral(n, seed 2077) used as MO integrals (default, SURVEY.md 8d) or the literal linear H_n chain, "
                          "STO-3G, 0.8 A, RHF orbitals (tencirchem_b200/hchain.py; the H4/H8/H12 molecules of BASELINE.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
+                    help="N>1: 'sharded' = one evaluation with the CI vector split by alpha rows (strong scaling); "
+                         "'replicas' = independent theta sets per rank (weak scaling)")
     ap.add_argument("--batch", type=int, default=0,
                     help="batched-theta mode: each step evaluates this many parameter sets in the same launches (small active spaces)")
     args = ap.parse_args()

@@ -31,7 +31,7 @@ class LocalComm:
         self.world = int(world)
         self.local_ranks = list(range(self.world))
 
-    def exchange(self, send: List[List["torch.Tensor"]]) -> List[List["torch.Tensor"]]:
+    def exchange(self, send: List[List["torch.Tensor"]], recv_counts=None) -> List[List["torch.Tensor"]]:
         # send[i][d]: rows that local rank i sends to rank d  ->  recv[i][s]: rows rank i receives from rank s
         return [[send[s][d] for s in range(self.world)] for d in range(self.world)]
 
@@ -54,24 +54,21 @@ class TorchComm:
         self.rank = dist.get_rank()
         self.local_ranks = [self.rank]
 
-    def exchange(self, send):
+    def exchange(self, send, recv_counts):
         import torch
 
         (mine,) = send
-        recv = [torch.empty(0)] * self.world
+        (counts,) = recv_counts  # rows to expect from every peer (both sides derive them from the layouts)
+        recv = [None] * self.world
         ops = []
-        counts = torch.tensor([t.shape[0] for t in mine], dtype=torch.int64, device=mine[self.rank].device)
-        all_counts = [torch.empty_like(counts) for _ in range(self.world)]
-        self.dist.all_gather(all_counts, counts)
         for peer in range(self.world):
             if peer == self.rank:
                 recv[peer] = mine[peer]
                 continue
-            n_in = int(all_counts[peer][self.rank])
-            recv[peer] = torch.empty((n_in,) + tuple(mine[peer].shape[1:]), dtype=mine[peer].dtype, device=mine[peer].device)
-            if mine[peer].numel():
+            recv[peer] = torch.empty((counts[peer],) + tuple(mine[peer].shape[1:]), dtype=mine[peer].dtype, device=mine[peer].device)
+            if mine[peer].shape[0]:
                 ops.append(self.dist.P2POp(self.dist.isend, mine[peer].contiguous(), peer))
-            if n_in:
+            if counts[peer]:
                 ops.append(self.dist.P2POp(self.dist.irecv, recv[peer], peer))
         if ops:
             for req in self.dist.batch_isend_irecv(ops):
@@ -125,7 +122,7 @@ class RowMover:
         self.reshards += 1
         plans = [self._move_plan(l_from, l_to, r) for r in self.comm.local_ranks]
         send = [[v.index_select(0, idx) for idx in mp[0]] for v, mp in zip(vecs, plans)]
-        recv = self.comm.exchange(send)
+        recv = self.comm.exchange(send, [[int(idx.numel()) for idx in mp[1]] for mp in plans])
         out = []
         for v, mp, got in zip(vecs, plans, recv):
             new = t.empty((mp[2],) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device)

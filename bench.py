@@ -190,7 +190,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": 1.0 / t_eval, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_eval, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong" if args.gpus > 1 and args.multi == "sharded" and args.batch == 0 else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_desc(n, args.ansatz, args.integrals), "note": "CPU oracle port of the reference numpy engine; each step is a bounded sample extrapolated by operation counts"},
         "cpu_baseline": {**res, "value": 1.0 / t_eval},
         "e2e": {"value": 1.0 / t_eval, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

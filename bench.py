@@ -217,6 +217,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     torch.cuda.init()
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = WORKLOADS[args.workload]
@@ -421,7 +422,7 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_desc(n, args.ansatz, args.integrals), "n_determinants": size, "n_excitations": m,
-                   "n_params": p_count, "l2": "inputs larger than L2" if size * 8 / world > 2.5e8 else "vectors fit in L2; no flush",
+                   "n_params": p_count, "l2": "inputs larger than L2 (ket + bra shards vs 126 MB)" if 2 * size * 8 / world > 1.26e8 else "vectors fit in L2; no flush",
                    "multi_gpu": f"one evaluation, CI vector sharded by alpha rows over {world} ranks; {reshards} row re-shards "
                                 f"(NCCL send/recv) per evaluation in {len(eng.segments)} segments; H.c by row blocks of the "
                                 "all-reduced vector; gradient and energy all-reduced",

@@ -35,6 +35,12 @@ class LocalComm:
         # send[i][d]: rows that local rank i sends to rank d  ->  recv[i][s]: rows rank i receives from rank s
         return [[send[s][d] for s in range(self.world)] for d in range(self.world)]
 
+    def exchange_packed(self, send_bufs, send_counts, recv_counts):
+        import torch
+
+        parts = [list(torch.split(b, list(c))) for b, c in zip(send_bufs, send_counts)]
+        return [torch.cat([parts[s][d] for s in range(self.world)]) for d in range(self.world)]
+
     def all_reduce_sum(self, tensors: List["torch.Tensor"]):
         total = tensors[0].clone()
         for t in tensors[1:]:
@@ -75,6 +81,20 @@ class TorchComm:
                 req.wait()
         return [recv]
 
+    def exchange_packed(self, send_bufs, send_counts, recv_counts):
+        """send_bufs[0]: rows grouped by destination rank ([sum(send_counts), nb]); returns the rows grouped by source.
+        One NCCL all-to-all; the gloo backend of the CPU tests has no all-to-all and takes the isend/irecv path."""
+        import torch
+
+        (buf,), (sc,), (rc,) = send_bufs, send_counts, recv_counts
+        out = torch.empty((sum(rc),) + tuple(buf.shape[1:]), dtype=buf.dtype, device=buf.device)
+        if self.dist.get_backend() == "nccl":
+            self.dist.all_to_all_single(out, buf, output_split_sizes=list(rc), input_split_sizes=list(sc))
+            return [out]
+        parts = list(torch.split(buf, list(sc)))
+        got = self.exchange([parts], [list(rc)])[0]
+        return [torch.cat(got)] if got else [out]
+
     def all_reduce_sum(self, tensors):
         (t,) = tensors
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
@@ -97,7 +117,16 @@ class RowMover:
         # rows[l][r]: storage rows of rank r in layout l, ascending (= its local row order)
         self.rows = [[np.nonzero(own == r)[0] for r in range(self.world)] for own in self.owner]
         self._moves = {}
+        self._rows_dev = {}
         self.reshards = 0
+
+    def rows_dev(self, layout: int, rank: int):
+        """Storage rows of `rank` in `layout` as an index tensor on the device (cached)."""
+        key = (layout, rank)
+        if key not in self._rows_dev:
+            t = self.torch
+            self._rows_dev[key] = t.as_tensor(self.rows[layout][rank], dtype=t.int64, device=self.device)
+        return self._rows_dev[key]
 
     def _move_plan(self, l_from: int, l_to: int, rank: int):
         key = (l_from, l_to, rank)
@@ -111,7 +140,8 @@ class RowMover:
                 in_rows = np.intersect1d(self.rows[l_from][peer], mine_to, assume_unique=True)
                 send_idx.append(t.as_tensor(np.searchsorted(mine_from, out_rows), dtype=t.int64, device=self.device))
                 recv_idx.append(t.as_tensor(np.searchsorted(mine_to, in_rows), dtype=t.int64, device=self.device))
-            self._moves[key] = (send_idx, recv_idx, len(mine_to))
+            self._moves[key] = (t.cat(send_idx), t.cat(recv_idx), len(mine_to), [int(i.numel()) for i in send_idx],
+                                [int(i.numel()) for i in recv_idx])
         return self._moves[key]
 
     def reshard(self, vecs: List["torch.Tensor"], l_from: int, l_to: int) -> List["torch.Tensor"]:
@@ -121,14 +151,14 @@ class RowMover:
             return vecs
         self.reshards += 1
         plans = [self._move_plan(l_from, l_to, r) for r in self.comm.local_ranks]
-        send = [[v.index_select(0, idx) for idx in mp[0]] for v, mp in zip(vecs, plans)]
-        recv = self.comm.exchange(send, [[int(idx.numel()) for idx in mp[1]] for mp in plans])
+        # pack the rows by destination (one gather), one all-to-all, unpack by local row (one scatter)
+        send = [v.index_select(0, mp[0]) for v, mp in zip(vecs, plans)]
+        recv = self.comm.exchange_packed(send, [mp[3] for mp in plans], [mp[4] for mp in plans])
         out = []
         for v, mp, got in zip(vecs, plans, recv):
             new = t.empty((mp[2],) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device)
-            for idx, rows in zip(mp[1], got):
-                if idx.numel():
-                    new.index_copy_(0, idx, rows)
+            if mp[1].numel():
+                new.index_copy_(0, mp[1], got)
             out.append(new)
         return out
 
@@ -198,7 +228,7 @@ class ShardedUCC:
         fulls = []
         for st, v in zip(self.states, vecs):
             full = t.zeros((self.na, self.nb), dtype=t.float64, device=self.device)
-            full[t.as_tensor(self.rows[layout][st.rank], dtype=t.int64, device=self.device)] = v
+            full.index_copy_(0, self.mover.rows_dev(layout, st.rank), v)
             fulls.append(full)
         self.comm.all_reduce_sum(fulls)
         return fulls
@@ -229,7 +259,7 @@ class ShardedUCC:
         self.comm.all_reduce_sum(s_full)
         bras, parts = [], []
         for st, sig, ket in zip(self.states, s_full, kets):
-            bra = sig[t.as_tensor(self.rows[layout][st.rank], dtype=t.int64, device=self.device)].contiguous()
+            bra = sig.index_select(0, self.mover.rows_dev(layout, st.rank))
             bras.append(bra)
             parts.append((bra * ket).sum().reshape(1))
         del s_full

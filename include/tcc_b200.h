@@ -172,6 +172,17 @@ int tcc_shard_gradient(tcc_plan* plan, double* grad_host /* [num_params] */, voi
 int tcc_apply_h_rows(tcc_plan* plan, const double* c_full_dev, double* sigma_full_dev, int64_t row_lo,
                      int64_t row_cnt, void* stream);
 
+/* Sharded sigma = H c (hamiltonian.py:146-155) with the vector kept distributed.  layouts3: the three row layouts
+ * (pairwise disjoint T) of the alpha-beta passes; layouts3[0] is the layout the forward sweep ends in. */
+int tcc_shard_sigma_layouts(const tcc_plan* plan, int32_t* layouts3);
+/* sigma_local += (beta-beta terms) c_local for `rows` local rows (any layout: these terms act inside a row) */
+int tcc_shard_sigma_bb(tcc_plan* plan, const double* c_local_dev, double* sigma_local_dev, int64_t rows, void* stream);
+/* sigma_cols = (alpha-alpha terms) c_cols on a block of `ncols` columns of ALL alpha rows, [num_strings, ncols] */
+int tcc_shard_sigma_aa(tcc_plan* plan, const double* c_cols_dev, double* sigma_cols_dev, int64_t ncols, void* stream);
+/* sigma_local += pass `pass` (0..2) of the alpha-beta terms: the alpha replacements E_pq that do not touch the
+ * orbitals T of layouts3[pass] (the first such layout per pair) keep every row on its rank */
+int tcc_shard_sigma_ab(tcc_plan* plan, int pass, const double* c_local_dev, double* sigma_local_dev, void* stream);
+
 /* ---- per-phase device timing (CUDA events on the call's stream, recorded only where the phase
  * changes).  Slots: forward rotations by kind, reverse-sweep steps by kind, the same-spin and
  * opposite-spin parts of H.c, the energy dot product.  `bytes` are ALGORITHMIC CI-vector bytes

@@ -66,6 +66,10 @@ SIGNATURES = {
     "tcc_shard_reverse": (C.c_int, [_p, C.c_int, _p, _p, _p]),
     "tcc_shard_gradient": (C.c_int, [_p, _dp, _p]),
     "tcc_apply_h_rows": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, _p]),
+    "tcc_shard_sigma_layouts": (C.c_int, [_p, _ip]),
+    "tcc_shard_sigma_bb": (C.c_int, [_p, _p, _p, C.c_int64, _p]),
+    "tcc_shard_sigma_aa": (C.c_int, [_p, _p, _p, C.c_int64, _p]),
+    "tcc_shard_sigma_ab": (C.c_int, [_p, C.c_int, _p, _p, _p]),
     "tcc_profile_enable": (C.c_int, [_p, C.c_int]),
     "tcc_profile_read": (C.c_int, [_p, _dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tcc_profile_batches": (C.c_int, [_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

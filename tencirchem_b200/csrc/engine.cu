@@ -160,6 +160,7 @@ struct tcc_plan {
     Link* d_links = nullptr;
     double* d_w = nullptr;
     double *rows_ws1 = nullptr, *rows_ws2 = nullptr;  // scratch of tcc_apply_h_rows
+    Link* d_sigma_links[3] = {nullptr, nullptr, nullptr};  // sharded sigma: alpha links per pass (local rows)
     size_t rows_ws_cap = 0;
     uint16_t* d_kmap = nullptr;  // beta link (p,q) -> row of the D intermediate
     bool w_pair_symmetric = false;
@@ -529,6 +530,7 @@ void tcc_plan_destroy(tcc_plan* p) {
     cudaFree(p->d_w);
     cudaFree(p->rows_ws1);
     cudaFree(p->rows_ws2);
+    for (int i = 0; i < 3; ++i) cudaFree(p->d_sigma_links[i]);
     cudaFree(p->d_kmap);
     cudaFree(p->d_ell_col);
     cudaFree(p->d_ell_val);
@@ -681,6 +683,17 @@ int tcc_set_hamiltonian(tcc_plan* p, const double* int1e, const double* int2e) {
     if (!p->d_links) {
         CUDA_TRY(dev_alloc(p, &p->d_links, hp.links.size()));
         CUDA_TRY(cudaMemcpy(p->d_links, hp.links.data(), hp.links.size() * sizeof(Link), cudaMemcpyHostToDevice));
+        if (hp.shard_world > 1) {
+            // sharded sigma: per-pass alpha link tables of this rank's rows (local target rows)
+            hp.build_sigma_pass_links();
+            for (int i = 0; i < 3; ++i) {
+                if (hp.sigma_links[i].empty()) continue;
+                CUDA_TRY(dev_alloc(p, &p->d_sigma_links[i], hp.sigma_links[i].size()));
+                CUDA_TRY(cudaMemcpy(p->d_sigma_links[i], hp.sigma_links[i].data(), hp.sigma_links[i].size() * sizeof(Link),
+                                    cudaMemcpyHostToDevice));
+                std::vector<Link>().swap(hp.sigma_links[i]);
+            }
+        }
     }
     CUDA_TRY(dev_alloc(p, &p->d_w, w.size()));
     CUDA_TRY(cudaMemcpy(p->d_w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1231,6 +1244,85 @@ int tcc_apply_h_rows(tcc_plan* p, const double* c_full_dev, double* sigma_full_d
     return 0;
 }
 
+
+// ---- sharded sigma = H c: the vector stays distributed ---------------------------------------------
+// beta-beta terms act inside a row: any layout.  alpha-beta terms: three passes, pass i in layout sigma_layout[i]
+// with the alpha replacements E_pq that do not touch that layout's orbitals T (they keep a row on its rank); three
+// layouts with disjoint T cover every pair.  alpha-alpha terms: on a column block of ALL rows (the caller transposes).
+int tcc_shard_sigma_layouts(const tcc_plan* p, int32_t* layouts3) {
+    if (!p || !layouts3) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    for (int i = 0; i < 3; ++i) layouts3[i] = p->hp.sigma_layout[i];
+    return 0;
+}
+
+static int ensure_rows_ws(tcc_plan* p, size_t need) {
+    if (p->rows_ws_cap >= need) return 0;
+    cudaFree(p->rows_ws1);
+    cudaFree(p->rows_ws2);
+    p->rows_ws1 = p->rows_ws2 = nullptr;
+    p->rows_ws_cap = 0;
+    CUDA_TRY(dev_alloc(p, &p->rows_ws1, need));
+    CUDA_TRY(dev_alloc(p, &p->rows_ws2, need));
+    p->rows_ws_cap = need;
+    return 0;
+}
+
+// sigma_local += (beta-beta part of H) c_local for `rows` local rows of any layout
+int tcc_shard_sigma_bb(tcc_plan* p, const double* c_local_dev, double* sigma_local_dev, int64_t rows, void* stream) {
+    if (!p || !c_local_dev || !sigma_local_dev || rows < 0) return fail(TCC_ERR_BAD_ARGUMENT, "bad argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    if (!p->has_h) return fail(TCC_ERR_NO_HAMILTONIAN, "tcc_set_hamiltonian has not been called");
+    HostPlan& hp = p->hp;
+    if (rows == 0) return 0;
+    cudaStream_t st = cudaStream_t(stream);
+    if (int rc = ensure_rows_ws(p, size_t(rows) * size_t(hp.nb))) return rc;
+    p->prof.mark(TCC_PROF_SIGMA_SS, st);
+    launch_transpose(c_local_dev, p->rows_ws1, rows, hp.nb, false, 1, st);
+    launch_spmm_rows(p->rows_ws1, p->rows_ws2, hp.nb, rows, p->d_ell_col, p->d_ell_val, hp.ell_width, false, 1, st);
+    launch_transpose(p->rows_ws2, sigma_local_dev, hp.nb, rows, true, 1, st);
+    p->prof.count(TCC_PROF_SIGMA_SS, 3, 7 * 8 * rows * hp.nb);
+    p->prof.mark(-1, st);
+    p->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// sigma_cols = (alpha-alpha part of H) c_cols on a block of `ncols` columns of ALL alpha rows ([na, ncols], storage rows)
+int tcc_shard_sigma_aa(tcc_plan* p, const double* c_cols_dev, double* sigma_cols_dev, int64_t ncols, void* stream) {
+    if (!p || !c_cols_dev || !sigma_cols_dev || ncols < 0) return fail(TCC_ERR_BAD_ARGUMENT, "bad argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    if (!p->has_h) return fail(TCC_ERR_NO_HAMILTONIAN, "tcc_set_hamiltonian has not been called");
+    HostPlan& hp = p->hp;
+    if (ncols == 0) return 0;
+    cudaStream_t st = cudaStream_t(stream);
+    p->prof.mark(TCC_PROF_SIGMA_SS, st);
+    launch_spmm_rows(c_cols_dev, sigma_cols_dev, hp.na, ncols, p->d_ell_col, p->d_ell_val, hp.ell_width, false, 1, st);
+    p->prof.count(TCC_PROF_SIGMA_SS, 1, 2 * 8 * hp.na * ncols);
+    p->prof.mark(-1, st);
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// sigma_local += pass `pass` of the alpha-beta part; c_local / sigma_local: the rank's rows in layout sigma_layout[pass]
+int tcc_shard_sigma_ab(tcc_plan* p, int pass, const double* c_local_dev, double* sigma_local_dev, void* stream) {
+    if (!p || pass < 0 || pass > 2 || !c_local_dev || !sigma_local_dev) return fail(TCC_ERR_BAD_ARGUMENT, "bad argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    if (!p->has_h) return fail(TCC_ERR_NO_HAMILTONIAN, "tcc_set_hamiltonian has not been called");
+    HostPlan& hp = p->hp;
+    if (hp.shard_world == 1) return fail(TCC_ERR_BAD_ARGUMENT, "not a sharded plan");
+    const int64_t rows = hp.layouts[hp.sigma_layout[pass]].rows[hp.shard_rank];
+    if (rows == 0 || hp.sigma_aml[pass] == 0) return 0;
+    cudaStream_t st = cudaStream_t(stream);
+    p->prof.mark(TCC_PROF_SIGMA_AB, st);
+    launch_sigma_ab(c_local_dev, sigma_local_dev, rows, hp.nb, p->d_links, hp.ml, p->d_w, hp.n, p->n2p, p->d_kmap, 1, st, 0, rows,
+                    p->d_sigma_links[pass], hp.sigma_aml[pass]);
+    p->prof.count(TCC_PROF_SIGMA_AB, (rows + 65534) / 65535, 3 * 8 * rows * hp.nb);
+    p->prof.mark(-1, st);
+    p->launches += (rows + 65534) / 65535;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
 
 int tcc_profile_batches(tcc_plan* p, int on, float* fwd_ms, float* rev_ms) {
     if (!p) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");

@@ -391,7 +391,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 
 __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict__ sigma, int64_t nb,
                                 const Link* __restrict__ links, int ml, const double* __restrict__ w, int n, int n2p,
-                                int64_t row0, int64_t set_stride, const uint16_t* __restrict__ kmap) {
+                                int64_t row0, int64_t set_stride, const uint16_t* __restrict__ kmap,
+                                const Link* __restrict__ alinks, int aml) {
+    // links / ml: single replacements of the beta strings (columns, always the full table); alinks / aml: those of the
+    // alpha strings = rows of c and sigma (the same table, or the filtered table with local rows of a sharded plan)
     // n2p = K of the GEMM: n^2 (padded) in general, n(n+1)/2 (padded) when W[pq,rs] == W[pq,sr] was verified at
     // set-up; kmap[p*n+q] = row of D that a forward beta link E_pq feeds
     extern __shared__ double dsm[];  // [n2p][SAB_LD]
@@ -416,12 +419,12 @@ __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-    const int mt_count = ml >> 3;
+    const int mt_count = aml >> 3;
     const int units = mt_count * (SAB_T / 16);
     const int g = lane >> 2, q4 = lane & 3;
     for (int u = warp; u < units; u += nwarps) {
         int mt = u / (SAB_T / 16), nh = u - mt * (SAB_T / 16);
-        Link rl = links[a * ml + mt * 8 + g];
+        Link rl = alinks[a * aml + mt * 8 + g];
         const double* wrow = w + int64_t(rl.pq) * n2p + q4;
         const double* dcol = dsm + q4 * SAB_LD + nh * 16 + g;
         double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
@@ -447,8 +450,14 @@ __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict
 }
 
 void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, const Link* links, int ml, const double* w,
-                     int n, int n2p, const uint16_t* kmap, int n_sets, cudaStream_t st, int64_t row_lo, int64_t row_cnt) {
-    int units = (ml / 8) * (SAB_T / 16);
+                     int n, int n2p, const uint16_t* kmap, int n_sets, cudaStream_t st, int64_t row_lo, int64_t row_cnt,
+                     const Link* alinks, int aml) {
+    if (!alinks) {
+        alinks = links;
+        aml = ml;
+    }
+    if (aml <= 0) return;
+    int units = (aml / 8) * (SAB_T / 16);
     int best_nw = 4;
     double best_eff = 0.0;
     for (int nw = 4; nw <= 16; ++nw) {
@@ -471,7 +480,7 @@ void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, con
     // grid.y is limited to 65535: launch in row batches
     for (int64_t r0 = r_begin; r0 < gy_total; r0 += 65535) {
         unsigned gy = unsigned(gy_total - r0 < 65535 ? gy_total - r0 : 65535);
-        sigma_ab_kernel<<<dim3(gx, gy, unsigned(n_sets)), best_nw * 32, smem, st>>>(c, sigma, nb, links, ml, w, n, n2p, r0, na * nb, kmap);
+        sigma_ab_kernel<<<dim3(gx, gy, unsigned(n_sets)), best_nw * 32, smem, st>>>(c, sigma, nb, links, ml, w, n, n2p, r0, na * nb, kmap, alinks, aml);
     }
 }
 

@@ -41,7 +41,7 @@ void launch_spmm_rows(const double* in, double* out, int64_t nrows, int64_t ncol
 // sigma(a', b') += sum_{pq,rs} W[pq,rs] <a'|E_pq|a><b'|E_rs|b> c(a,b)  (opposite-spin part, DMMA)
 void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, const Link* links, int ml,
                      const double* w, int n, int n2p, const uint16_t* kmap, int n_sets, cudaStream_t st, int64_t row_lo = 0,
-                     int64_t row_cnt = -1);
+                     int64_t row_cnt = -1, const Link* alinks = nullptr, int aml = 0);
 // hard-core-boson sigma (hamiltonian.py:158-183)
 void launch_sigma_hcb(const double* c, double* sigma, int64_t nstr, const uint32_t* strings, int n, int k,
                       const double* diag1, const double* hop, const double* diag2, const int64_t* binom,

@@ -692,8 +692,69 @@ void HostPlan::choose_row_layouts() {
             segments.back().batch_hi = b + 1;
     }
     if (layouts.empty()) layouts.push_back(make_layout(t ? (1u << t) - 1 : 0));
+    // layouts of the sharded sigma: the layout the forward sweep ends in, and two more with disjoint T
+    sigma_layout[0] = segments.empty() ? 0 : segments.back().layout;
+    uint32_t used = layouts[sigma_layout[0]].T;
+    for (int i = 1; i < 3; ++i) {
+        uint32_t T = 0;
+        int cnt = 0;
+        for (int o = n - 1; o >= 0 && cnt < t; --o)
+            if (!(used >> o & 1)) {
+                T |= 1u << o;
+                ++cnt;
+            }
+        used |= T;
+        auto it = layout_of.find(T);
+        if (it == layout_of.end()) {
+            it = layout_of.emplace(T, int(layouts.size())).first;
+            layouts.push_back(make_layout(T));
+        }
+        sigma_layout[i] = it->second;
+    }
     max_local_rows = 0;
     for (const auto& L : layouts) max_local_rows = std::max(max_local_rows, L.rows[shard_rank]);
+}
+
+void HostPlan::build_sigma_pass_links() {
+    if (shard_world == 1 || links.empty()) return;
+    for (int pass = 0; pass < 3; ++pass) {
+        const RowLayout& L = layouts[sigma_layout[pass]];
+        auto pass_of = [&](int p, int q) {
+            for (int i = 0; i < 3; ++i) {
+                const uint32_t T = layouts[sigma_layout[i]].T;
+                if (!(T >> p & 1) && !(T >> q & 1)) return i;
+            }
+            return -1;  // cannot happen: a pair touches at most two of three disjoint sets
+        };
+        const int64_t rows = L.rows[shard_rank];
+        // longest filtered list
+        int longest = 0;
+        for (int64_t a = 0; a < nstr; ++a) {
+            if (L.owner[a] != shard_rank) continue;
+            int c = 0;
+            for (int l = 0; l < ml; ++l) {
+                const Link& lk = links[size_t(a) * ml + l];
+                if (lk.sgn != 0 && (lk.pq / n == lk.pq % n ? pass == 0 : pass_of(lk.pq / n, lk.pq % n) == pass)) ++c;
+            }
+            longest = std::max(longest, c);
+        }
+        const int aml = (longest + 7) / 8 * 8;
+        sigma_aml[pass] = aml;
+        sigma_links[pass].assign(size_t(rows) * aml, Link{0, 0, 0, 0});
+        for (int64_t a = 0; a < nstr; ++a) {
+            if (L.owner[a] != shard_rank) continue;
+            Link* dst = sigma_links[pass].data() + size_t(L.local_row[a]) * aml;
+            int c = 0;
+            for (int l = 0; l < ml; ++l) {
+                const Link& lk = links[size_t(a) * ml + l];
+                if (lk.sgn == 0) continue;
+                const int p = lk.pq / n, q = lk.pq % n;
+                if (!(p == q ? pass == 0 : pass_of(p, q) == pass)) continue;
+                // E_pq with p, q outside T keeps the occupation pattern on T: the target row is on this rank
+                dst[c++] = Link{L.local_row[lk.addr], lk.pq, lk.sgn, 0};
+            }
+        }
+    }
 }
 
 void HostPlan::finalize(int tile_elems, bool use_layout, int rank, int world) {

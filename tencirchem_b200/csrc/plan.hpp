@@ -137,6 +137,12 @@ struct HostPlan {
     int shard_rank = 0, shard_world = 1;
     std::vector<RowLayout> layouts;
     std::vector<Segment> segments;
+    // sharded sigma: three layouts with pairwise disjoint T; an alpha replacement E_pq is contracted in the first of
+    // them whose T it does not touch (there it maps a row to a row of the same rank)
+    int sigma_layout[3] = {0, 0, 0};
+    int sigma_aml[3] = {0, 0, 0};
+    std::vector<Link> sigma_links[3];  // [local rows of the pass layout][sigma_aml], addr = LOCAL target row
+    void build_sigma_pass_links();
     int64_t max_local_rows = 0;  // over the layouts, for this rank
     int shard_bits() const {
         int t = 0;

@@ -156,6 +156,23 @@ class Plan:
         _lib.check(self.lib.tcc_apply_h_rows(self.handle, C.c_void_p(c_full.data_ptr()), C.c_void_p(sigma_full.data_ptr()),
                                              int(row_lo), int(row_cnt), self._stream()))
 
+    def shard_sigma_layouts(self):
+        out = np.zeros(3, dtype=np.int32)
+        _lib.check(self.lib.tcc_shard_sigma_layouts(self.handle, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return [int(x) for x in out]
+
+    def shard_sigma_bb(self, c_local, sigma_local):
+        _lib.check(self.lib.tcc_shard_sigma_bb(self.handle, self._ptr(c_local), self._ptr(sigma_local), int(c_local.shape[0]),
+                                               self._stream()))
+
+    def shard_sigma_aa(self, c_cols, sigma_cols):
+        _lib.check(self.lib.tcc_shard_sigma_aa(self.handle, self._ptr(c_cols), self._ptr(sigma_cols), int(c_cols.shape[1]),
+                                               self._stream()))
+
+    def shard_sigma_ab(self, pass_id: int, c_local, sigma_local):
+        _lib.check(self.lib.tcc_shard_sigma_ab(self.handle, int(pass_id), self._ptr(c_local), self._ptr(sigma_local),
+                                               self._stream()))
+
     def to_storage_order_dev(self, ref, out):
         """out (storage order) <- ref (reference order); full CI vectors on the device."""
         _lib.check(self.lib.tcc_to_storage_order(self.handle, self._ptr(ref), self._ptr(out), self._stream()))

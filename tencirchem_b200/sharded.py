@@ -163,6 +163,55 @@ class RowMover:
         return out
 
 
+    # ---- row-sharded [rows, nb]  <->  column-sharded [na, cols] (all rows, a block of columns) ----------------
+    def col_bounds(self, rank: int):
+        return shard_bounds(self.nb, rank, self.world)
+
+    def to_columns(self, vecs, layout: int):
+        """vecs[i]: [rows of local rank i in `layout`, nb] -> [na, columns of that rank] (storage row order)."""
+        t = self.torch
+        na = len(self.owner[layout])
+        send, sc, rc = [], [], []
+        for v, r in zip(vecs, self.comm.local_ranks):
+            parts = [v[:, lo:hi].reshape(-1) for lo, hi in (self.col_bounds(d) for d in range(self.world))]
+            send.append(t.cat(parts))
+            sc.append([int(x.numel()) for x in parts])
+            lo, hi = self.col_bounds(r)
+            rc.append([len(self.rows[layout][s_]) * (hi - lo) for s_ in range(self.world)])
+        recv = self.comm.exchange_packed(send, sc, rc)
+        out = []
+        for r, got, counts in zip(self.comm.local_ranks, recv, rc):
+            lo, hi = self.col_bounds(r)
+            full = t.empty((na, hi - lo), dtype=got.dtype, device=self.device)
+            for s_, blk in enumerate(t.split(got, counts)):
+                if blk.numel():
+                    full.index_copy_(0, self.rows_dev(layout, s_), blk.reshape(-1, hi - lo))
+            out.append(full)
+        return out
+
+    def to_rows(self, cols, layout: int):
+        """Inverse of to_columns: [na, columns of local rank i] -> [rows of that rank in `layout`, nb]."""
+        t = self.torch
+        send, sc, rc = [], [], []
+        for c, r in zip(cols, self.comm.local_ranks):
+            parts = [c.index_select(0, self.rows_dev(layout, d)).reshape(-1) for d in range(self.world)]
+            send.append(t.cat(parts))
+            sc.append([int(x.numel()) for x in parts])
+            n_rows = len(self.rows[layout][r])
+            rc.append([n_rows * (hi - lo) for lo, hi in (self.col_bounds(s_) for s_ in range(self.world))])
+        recv = self.comm.exchange_packed(send, sc, rc)
+        out = []
+        for r, got, counts in zip(self.comm.local_ranks, recv, rc):
+            n_rows = len(self.rows[layout][r])
+            new = t.empty((n_rows, self.nb), dtype=got.dtype, device=self.device)
+            for s_, blk in enumerate(t.split(got, counts)):
+                lo, hi = self.col_bounds(s_)
+                if blk.numel():
+                    new[:, lo:hi] = blk.reshape(n_rows, hi - lo)
+            out.append(new)
+        return out
+
+
 class _RankState:
     def __init__(self, plan: Plan, rank: int):
         self.plan = plan
@@ -172,9 +221,14 @@ class _RankState:
 class ShardedUCC:
     """energy / energy_and_grad / civector of one ansatz with the CI vector sharded over `comm.world` ranks."""
 
-    def __init__(self, n_qubits, n_elec, ex_ops, param_ids, comm, device=0):
+    def __init__(self, n_qubits, n_elec, ex_ops, param_ids, comm, device=0, sigma_mode="distributed"):
+        """sigma_mode: "distributed" keeps the vector sharded through H c (three alpha-beta passes + a column
+        transpose for the alpha-alpha terms); "replicated" all-reduces the full vector (needs 2 full vectors per GPU)."""
         import torch
 
+        if sigma_mode not in ("distributed", "replicated"):
+            raise ValueError("sigma_mode must be 'distributed' or 'replicated'")
+        self.sigma_mode = sigma_mode if comm.world > 1 else "replicated"
         self.torch = torch
         self.comm = comm
         self.world = comm.world
@@ -233,6 +287,45 @@ class ShardedUCC:
         self.comm.all_reduce_sum(fulls)
         return fulls
 
+    def _sigma_distributed(self, kets, layout):
+        """sigma = H c with the vector kept sharded (include/tcc_b200.h, sharded sigma): kets in `layout` -> bras in
+        the same layout.  Needs no full vector on any rank."""
+        t = self.torch
+        l3 = self.states[0].plan.shard_sigma_layouts()
+        sig = []
+        for st, ket in zip(self.states, kets):
+            s_loc = t.zeros_like(ket)
+            if ket.numel():
+                st.plan.shard_sigma_bb(ket, s_loc)
+            sig.append(s_loc)
+        # alpha-beta: pass i in layout l3[i]
+        for i, l in enumerate(l3):
+            c_i = self._reshard(kets, layout, l)
+            part = []
+            for st, c in zip(self.states, c_i):
+                s_i = t.zeros_like(c)
+                if c.numel():
+                    st.plan.shard_sigma_ab(i, c, s_i)
+                part.append(s_i)
+            del c_i
+            part = self._reshard(part, l, layout)
+            for s_loc, s_i in zip(sig, part):
+                s_loc += s_i
+            del part
+        # alpha-alpha: on column blocks of all rows
+        cols = self.mover.to_columns(kets, layout)
+        s_cols = []
+        for st, c in zip(self.states, cols):
+            out = t.empty_like(c)
+            if c.numel():
+                st.plan.shard_sigma_aa(c, out)
+            s_cols.append(out)
+        del cols
+        back = self.mover.to_rows(s_cols, layout)
+        for s_loc, s_i in zip(sig, back):
+            s_loc += s_i
+        return sig
+
     def civector(self, params) -> np.ndarray:
         """Reference-order CI vector on the host (small systems / tests: gathers the full vector)."""
         t = self.torch
@@ -247,22 +340,22 @@ class ShardedUCC:
         t = self.torch
         params = np.asarray(params, dtype=np.float64)
         kets, layout = self._forward(params)
-        # sigma = H c: every rank contracts a block of rows of the gathered vector; the blocks are summed
-        c_full = self._gather_full(kets, layout)
-        s_full = []
-        for st, c in zip(self.states, c_full):
-            sig = t.zeros_like(c)
-            lo, hi = shard_bounds(self.na, st.rank, self.world)
-            st.plan.apply_h_rows(c, sig, lo, hi - lo)
-            s_full.append(sig)
-        del c_full
-        self.comm.all_reduce_sum(s_full)
-        bras, parts = [], []
-        for st, sig, ket in zip(self.states, s_full, kets):
-            bra = sig.index_select(0, self.mover.rows_dev(layout, st.rank))
-            bras.append(bra)
-            parts.append((bra * ket).sum().reshape(1))
-        del s_full
+        if self.sigma_mode == "distributed":
+            bras = self._sigma_distributed(kets, layout)
+        else:
+            # sigma = H c: every rank contracts a block of rows of the gathered vector; the blocks are summed
+            c_full = self._gather_full(kets, layout)
+            s_full = []
+            for st, c in zip(self.states, c_full):
+                sig = t.zeros_like(c)
+                lo, hi = shard_bounds(self.na, st.rank, self.world)
+                st.plan.apply_h_rows(c, sig, lo, hi - lo)
+                s_full.append(sig)
+            del c_full
+            self.comm.all_reduce_sum(s_full)
+            bras = [sig.index_select(0, self.mover.rows_dev(layout, st.rank)) for st, sig in zip(self.states, s_full)]
+            del s_full
+        parts = [(bra * ket).sum().reshape(1) for bra, ket in zip(bras, kets)]
         self.comm.all_reduce_sum(parts)
         energy = float(parts[0][0])
         if not want_grad:

@@ -549,17 +549,19 @@ def test_sharded_virtual_ranks_match_oracle(world, tile_elems, monkeypatch):
     for kind, no, nv in [("uccsd", 3, 3), ("uccsd", 4, 4), ("kupccgsd", 3, 3)]:
         ucc, int1e, int2e = _build(kind, no, nv)
         params = _params(ucc.n_params)
-        eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, LocalComm(world))
-        eng.set_hamiltonian(int1e, int2e)
         h = O.get_h_from_integral(int1e, int2e, ucc.n_elec, False)
         e_ref, g_ref = O.get_energy_and_grad(params, h, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False)
         c_ref = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False)
-        assert np.abs(eng.civector(params) - c_ref).max() < C_TOL
-        e, g = eng.energy_and_grad(params)
-        assert abs(e - e_ref) < E_TOL
-        assert np.abs(g - g_ref).max() < G_TOL
-        if world > 1 and kind == "uccsd":
-            assert eng.reshards > 0  # the layouts really changed
+        # H c either with the vector kept sharded (three alpha-beta passes + column transpose) or all-reduced
+        for sigma_mode in (("distributed", "replicated") if world > 1 else ("replicated",)):
+            eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, LocalComm(world), sigma_mode=sigma_mode)
+            eng.set_hamiltonian(int1e, int2e)
+            assert np.abs(eng.civector(params) - c_ref).max() < C_TOL
+            e, g = eng.energy_and_grad(params)
+            assert abs(e - e_ref) < E_TOL, (sigma_mode, e, e_ref)
+            assert np.abs(g - g_ref).max() < G_TOL, sigma_mode
+            if world > 1 and kind == "uccsd":
+                assert eng.reshards > 0  # the layouts really changed
         O.clear_cache()
 
 

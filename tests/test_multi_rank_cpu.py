@@ -93,6 +93,12 @@ def _reshard_worker(rank, world, port, out):
         local = mover.reshard(local, layout, l)
         layout = l
         ok = ok and torch.equal(local[0], full[torch.as_tensor(mover.rows[l][rank])])
+    # row-sharded <-> column-sharded (the transposes of the sharded alpha-alpha sigma)
+    lo, hi = mover.col_bounds(rank)
+    cols = mover.to_columns(local, layout)
+    ok = ok and torch.equal(cols[0], full[:, lo:hi])
+    back = mover.to_rows(cols, layout)
+    ok = ok and torch.equal(back[0], local[0])
     # ownership is a partition of the rows in every layout
     for own in mover.owner:
         ok = ok and own.min() >= 0 and own.max() < world and len(own) == na

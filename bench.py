@@ -363,7 +363,7 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
     torch.cuda.empty_cache()
     m, p_count, size = len(ucc.ex_ops), ucc.n_params, ucc.civector_size
     t0 = time.perf_counter()
-    eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, TorchComm(), device=local_rank)
+    eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, TorchComm(), device=local_rank, sigma_mode=args.sigma)
     eng.set_hamiltonian(int1e, int2e)
     staging_s = time.perf_counter() - t0
     plan = eng.states[0].plan
@@ -424,8 +424,11 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
         "config": {"workload": workload_desc(n, args.ansatz, args.integrals), "n_determinants": size, "n_excitations": m,
                    "n_params": p_count, "l2": "inputs larger than L2 (ket + bra shards vs 126 MB)" if 2 * size * 8 / world > 1.26e8 else "vectors fit in L2; no flush",
                    "multi_gpu": f"one evaluation, CI vector sharded by alpha rows over {world} ranks; {reshards} row re-shards "
-                                f"(NCCL send/recv) per evaluation in {len(eng.segments)} segments; H.c by row blocks of the "
-                                "all-reduced vector; gradient and energy all-reduced",
+                                f"(NCCL all-to-all) per evaluation in {len(eng.segments)} segments; "
+                                + ("H.c with the vector kept sharded (3 alpha-beta passes on per-layout link tables, alpha-alpha on "
+                                   "column blocks, beta-beta local)" if eng.sigma_mode == "distributed" else
+                                   "H.c by row blocks of the all-reduced vector")
+                                + "; gradient and energy all-reduced",
                    "n_batches": plan.n_batches, "staging_s": round(staging_s, 2)},
         "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": 8 * p_count * world,
                 "d2h_bytes_per_step": 8 * (m + 1) * world,
@@ -528,6 +531,8 @@ def main():
                     help="random_integral(n, seed 2077) used as MO integrals (default, SURVEY.md 8d) or the literal linear H_n chain, "
                          "STO-3G, 0.8 A, RHF orbitals (tencirchem_b200/hchain.py; the H4/H8/H12 molecules of BASELINE.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sigma", default="auto", choices=["auto", "distributed", "replicated"],
+                    help="N>1 sharded runs: H.c with the vector kept sharded, or on the all-reduced full vector")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: 'sharded' = one evaluation with the CI vector split by alpha rows (strong scaling); "
                          "'replicas' = independent theta sets per rank (weak scaling)")

@@ -104,10 +104,11 @@ class RowMover:
     """Moves the rows of local [rows, nb] matrices between the row layouts of a sharded plan.  Host logic only
     (index maps from `tcc_shard_layout`); the tensors may live on the GPU (NCCL) or on the CPU (gloo tests)."""
 
-    def __init__(self, plan: Plan, comm, device):
+    def __init__(self, plan: Plan, comm, device, chunk_bytes: int = 4 << 30):
         import torch
 
         self.torch = torch
+        self.chunk_bytes = int(chunk_bytes)
         self.comm = comm
         self.world = comm.world
         self.device = device
@@ -134,14 +135,24 @@ class RowMover:
             t = self.torch
             mine_from = self.rows[l_from][rank]
             mine_to = self.rows[l_to][rank]
+            n_max = max(max(len(r) for r in self.rows[l_from]), 1)
+            # the move runs in `pieces` rounds so that the staging buffers stay below chunk_bytes (every rank derives
+            # the same number of rounds and the same split of every (source, destination) row list)
+            pieces = max(1, -(-(n_max * self.nb * 8) // self.chunk_bytes))
             send_idx, recv_idx = [], []
             for peer in range(self.world):
                 out_rows = np.intersect1d(mine_from, self.rows[l_to][peer], assume_unique=True)
                 in_rows = np.intersect1d(self.rows[l_from][peer], mine_to, assume_unique=True)
-                send_idx.append(t.as_tensor(np.searchsorted(mine_from, out_rows), dtype=t.int64, device=self.device))
-                recv_idx.append(t.as_tensor(np.searchsorted(mine_to, in_rows), dtype=t.int64, device=self.device))
-            self._moves[key] = (t.cat(send_idx), t.cat(recv_idx), len(mine_to), [int(i.numel()) for i in send_idx],
-                                [int(i.numel()) for i in recv_idx])
+                send_idx.append(np.array_split(np.searchsorted(mine_from, out_rows), pieces))
+                recv_idx.append(np.array_split(np.searchsorted(mine_to, in_rows), pieces))
+            rounds = []
+            for j in range(pieces):
+                s_j = [send_idx[peer][j] for peer in range(self.world)]
+                r_j = [recv_idx[peer][j] for peer in range(self.world)]
+                rounds.append((t.as_tensor(np.concatenate(s_j), dtype=t.int64, device=self.device),
+                               t.as_tensor(np.concatenate(r_j), dtype=t.int64, device=self.device),
+                               [len(x) for x in s_j], [len(x) for x in r_j]))
+            self._moves[key] = (rounds, len(mine_to))
         return self._moves[key]
 
     def reshard(self, vecs: List["torch.Tensor"], l_from: int, l_to: int) -> List["torch.Tensor"]:
@@ -151,37 +162,43 @@ class RowMover:
             return vecs
         self.reshards += 1
         plans = [self._move_plan(l_from, l_to, r) for r in self.comm.local_ranks]
-        # pack the rows by destination (one gather), one all-to-all, unpack by local row (one scatter)
-        send = [v.index_select(0, mp[0]) for v, mp in zip(vecs, plans)]
-        recv = self.comm.exchange_packed(send, [mp[3] for mp in plans], [mp[4] for mp in plans])
-        out = []
-        for v, mp, got in zip(vecs, plans, recv):
-            new = t.empty((mp[2],) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device)
-            if mp[1].numel():
-                new.index_copy_(0, mp[1], got)
-            out.append(new)
+        out = [t.empty((mp[1],) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device) for v, mp in zip(vecs, plans)]
+        for j in range(len(plans[0][0])):
+            rnd = [mp[0][j] for mp in plans]
+            # pack the rows by destination (one gather), one all-to-all, unpack by local row (one scatter)
+            send = [v.index_select(0, r_[0]) for v, r_ in zip(vecs, rnd)]
+            recv = self.comm.exchange_packed(send, [r_[2] for r_ in rnd], [r_[3] for r_ in rnd])
+            for new, r_, got in zip(out, rnd, recv):
+                if r_[1].numel():
+                    new.index_copy_(0, r_[1], got)
         return out
 
-
     # ---- row-sharded [rows, nb]  <->  column-sharded [na, cols] (all rows, a block of columns) ----------------
-    def col_bounds(self, rank: int):
-        return shard_bounds(self.nb, rank, self.world)
+    def col_bounds(self, rank: int, piece: int = 0, pieces: int = 1):
+        """Columns of `rank` (contiguous, balanced); with pieces > 1 the `piece`-th part of that block."""
+        lo, hi = shard_bounds(self.nb, rank, self.world)
+        plo, phi = shard_bounds(hi - lo, piece, pieces)
+        return lo + plo, lo + phi
 
-    def to_columns(self, vecs, layout: int):
-        """vecs[i]: [rows of local rank i in `layout`, nb] -> [na, columns of that rank] (storage row order)."""
+    def column_pieces(self, layout: int) -> int:
+        n_max = max(max(len(r) for r in self.rows[layout]), 1)
+        return max(1, -(-(n_max * self.nb * 8) // self.chunk_bytes))
+
+    def to_columns(self, vecs, layout: int, piece: int = 0, pieces: int = 1):
+        """vecs[i]: [rows of local rank i in `layout`, nb] -> [na, (piece of the) columns of that rank], storage rows."""
         t = self.torch
         na = len(self.owner[layout])
         send, sc, rc = [], [], []
         for v, r in zip(vecs, self.comm.local_ranks):
-            parts = [v[:, lo:hi].reshape(-1) for lo, hi in (self.col_bounds(d) for d in range(self.world))]
+            parts = [v[:, lo:hi].reshape(-1) for lo, hi in (self.col_bounds(d, piece, pieces) for d in range(self.world))]
             send.append(t.cat(parts))
             sc.append([int(x.numel()) for x in parts])
-            lo, hi = self.col_bounds(r)
+            lo, hi = self.col_bounds(r, piece, pieces)
             rc.append([len(self.rows[layout][s_]) * (hi - lo) for s_ in range(self.world)])
         recv = self.comm.exchange_packed(send, sc, rc)
         out = []
         for r, got, counts in zip(self.comm.local_ranks, recv, rc):
-            lo, hi = self.col_bounds(r)
+            lo, hi = self.col_bounds(r, piece, pieces)
             full = t.empty((na, hi - lo), dtype=got.dtype, device=self.device)
             for s_, blk in enumerate(t.split(got, counts)):
                 if blk.numel():
@@ -189,8 +206,9 @@ class RowMover:
             out.append(full)
         return out
 
-    def to_rows(self, cols, layout: int):
-        """Inverse of to_columns: [na, columns of local rank i] -> [rows of that rank in `layout`, nb]."""
+    def to_rows(self, cols, layout: int, piece: int = 0, pieces: int = 1, add_into=None):
+        """Inverse of to_columns.  Returns new [rows, nb] matrices (pieces == 1), or ADDS the received column blocks
+        into add_into[i] (the accumulation of the alpha-alpha sigma, piece by piece)."""
         t = self.torch
         send, sc, rc = [], [], []
         for c, r in zip(cols, self.comm.local_ranks):
@@ -198,16 +216,16 @@ class RowMover:
             send.append(t.cat(parts))
             sc.append([int(x.numel()) for x in parts])
             n_rows = len(self.rows[layout][r])
-            rc.append([n_rows * (hi - lo) for lo, hi in (self.col_bounds(s_) for s_ in range(self.world))])
+            rc.append([n_rows * (hi - lo) for lo, hi in (self.col_bounds(s_, piece, pieces) for s_ in range(self.world))])
         recv = self.comm.exchange_packed(send, sc, rc)
         out = []
-        for r, got, counts in zip(self.comm.local_ranks, recv, rc):
+        for i, (r, got, counts) in enumerate(zip(self.comm.local_ranks, recv, rc)):
             n_rows = len(self.rows[layout][r])
-            new = t.empty((n_rows, self.nb), dtype=got.dtype, device=self.device)
+            new = add_into[i] if add_into is not None else t.zeros((n_rows, self.nb), dtype=got.dtype, device=self.device)
             for s_, blk in enumerate(t.split(got, counts)):
-                lo, hi = self.col_bounds(s_)
+                lo, hi = self.col_bounds(s_, piece, pieces)
                 if blk.numel():
-                    new[:, lo:hi] = blk.reshape(n_rows, hi - lo)
+                    new[:, lo:hi] += blk.reshape(n_rows, hi - lo)
             out.append(new)
         return out
 
@@ -221,13 +239,22 @@ class _RankState:
 class ShardedUCC:
     """energy / energy_and_grad / civector of one ansatz with the CI vector sharded over `comm.world` ranks."""
 
-    def __init__(self, n_qubits, n_elec, ex_ops, param_ids, comm, device=0, sigma_mode="distributed"):
+    def __init__(self, n_qubits, n_elec, ex_ops, param_ids, comm, device=0, sigma_mode="auto", chunk_bytes=4 << 30):
         """sigma_mode: "distributed" keeps the vector sharded through H c (three alpha-beta passes + a column
-        transpose for the alpha-alpha terms); "replicated" all-reduces the full vector (needs 2 full vectors per GPU)."""
+        transpose for the alpha-alpha terms); "replicated" all-reduces the full vector (2 full vectors per GPU; faster:
+        one pass of the opposite-spin kernel); "auto" = replicated while two full vectors take less than a quarter of
+        the GPU's memory, distributed beyond ((20e,20o): 273 GB per vector)."""
         import torch
 
-        if sigma_mode not in ("distributed", "replicated"):
-            raise ValueError("sigma_mode must be 'distributed' or 'replicated'")
+        if sigma_mode not in ("auto", "distributed", "replicated"):
+            raise ValueError("sigma_mode must be 'auto', 'distributed' or 'replicated'")
+        if sigma_mode == "auto":
+            from math import comb
+
+            n = n_qubits // 2
+            full_bytes = 8 * comb(n, n_elec // 2) ** 2
+            total = torch.cuda.get_device_properties(int(device)).total_memory
+            sigma_mode = "replicated" if 2 * full_bytes < total // 4 else "distributed"
         self.sigma_mode = sigma_mode if comm.world > 1 else "replicated"
         self.torch = torch
         self.comm = comm
@@ -239,7 +266,7 @@ class ShardedUCC:
         self.n_params, self.na = p0.n_params, p0.n_strings
         self.nb = p0.n_strings
         self.segments = p0.shard_segments()
-        self.mover = RowMover(p0, comm, self.device)
+        self.mover = RowMover(p0, comm, self.device, chunk_bytes)
         self.rows = self.mover.rows
         self.hf_row = int(p0.storage_order()[0])  # HF determinant = reference address 0 of both spins
 
@@ -312,18 +339,19 @@ class ShardedUCC:
             for s_loc, s_i in zip(sig, part):
                 s_loc += s_i
             del part
-        # alpha-alpha: on column blocks of all rows
-        cols = self.mover.to_columns(kets, layout)
-        s_cols = []
-        for st, c in zip(self.states, cols):
-            out = t.empty_like(c)
-            if c.numel():
-                st.plan.shard_sigma_aa(c, out)
-            s_cols.append(out)
-        del cols
-        back = self.mover.to_rows(s_cols, layout)
-        for s_loc, s_i in zip(sig, back):
-            s_loc += s_i
+        # alpha-alpha: on column blocks of all rows (in pieces, so that the transposed copies stay small)
+        pieces = self.mover.column_pieces(layout)
+        for j in range(pieces):
+            cols = self.mover.to_columns(kets, layout, j, pieces)
+            s_cols = []
+            for st, c in zip(self.states, cols):
+                out = t.empty_like(c)
+                if c.numel():
+                    st.plan.shard_sigma_aa(c, out)
+                s_cols.append(out)
+            del cols
+            self.mover.to_rows(s_cols, layout, j, pieces, add_into=sig)
+            del s_cols
         return sig
 
     def civector(self, params) -> np.ndarray:

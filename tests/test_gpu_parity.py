@@ -554,7 +554,9 @@ def test_sharded_virtual_ranks_match_oracle(world, tile_elems, monkeypatch):
         c_ref = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False)
         # H c either with the vector kept sharded (three alpha-beta passes + column transpose) or all-reduced
         for sigma_mode in (("distributed", "replicated") if world > 1 else ("replicated",)):
-            eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, LocalComm(world), sigma_mode=sigma_mode)
+            # a small staging budget forces the row moves and the column transposes to run in several rounds
+            eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, LocalComm(world), sigma_mode=sigma_mode,
+                             chunk_bytes=(4 << 30) if tile_elems == 6144 else 1024)
             eng.set_hamiltonian(int1e, int2e)
             assert np.abs(eng.civector(params) - c_ref).max() < C_TOL
             e, g = eng.energy_and_grad(params)

@@ -81,7 +81,7 @@ def _reshard_worker(rank, world, port, out):
 
     ex_ops, param_ids = pools.uccsd_ex_ops(3, 3)[:2]
     plan = Plan(12, 6, ex_ops, param_ids, device=None, shard=(rank, world))  # host-only: schedule + layouts
-    mover = RowMover(plan, TorchComm(), torch.device("cpu"))
+    mover = RowMover(plan, TorchComm(), torch.device("cpu"), chunk_bytes=512)  # several rounds per move
     na = plan.n_strings
     full = torch.arange(na * na, dtype=torch.float64).reshape(na, na)  # full[a, b] identifies its element
     segs = plan.shard_segments()

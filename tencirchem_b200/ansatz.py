@@ -85,6 +85,23 @@ class UCC:
         self.scipy_minimize_options = None
         self.opt_res = None
         self.params = None
+        self._sharded = None
+
+    def shard(self, comm, device: int = 0, **kwargs):
+        """Spread the CI vector of this ansatz over the ranks of `comm` (tencirchem_b200.sharded: alpha-row sharding,
+        one process per GPU with `TorchComm()`, or `LocalComm(n)` for n virtual ranks on one GPU).  Afterwards
+        `civector`, `energy`, `energy_and_grad` and `kernel` run on the sharded engine; every rank gets the same
+        results, so the L-BFGS-B drivers of all ranks take the same path."""
+        from .sharded import ShardedUCC
+
+        self._sanity_check()
+        if self.hcb:
+            raise ValueError("hcb (pUCCD) vectors have a single alpha row and are not sharded")
+        if self.init_state is not None:
+            raise ValueError("the sharded engine starts from the HF determinant; init_state is not supported")
+        self._sharded = ShardedUCC(self.n_qubits, self.n_elec, self.ex_ops, self.param_ids, comm, device=device, **kwargs)
+        self._sharded.set_hamiltonian(self.int1e, self.int2e)
+        return self
 
     @classmethod
     def from_integral(cls, int1e, int2e, n_elec, e_core: float = 0, **kwargs):
@@ -163,6 +180,8 @@ class UCC:
         self._sanity_check()
         params = self._check_params_argument(params)
         self._check_engine(engine)
+        if self._sharded is not None:
+            return self._sharded.civector(params)
         return engine_ucc.get_civector(params, self.n_qubits, self.n_elec, self.ex_ops, self.param_ids, self.hcb, self.init_state)
 
     def energy(self, params=None, engine: str = None) -> float:
@@ -172,6 +191,8 @@ class UCC:
         self._check_engine(engine)
         if params is self.params and self.opt_res is not None:
             return self.opt_res["e"]
+        if self._sharded is not None:
+            return float(self._sharded.energy(params)) + self.e_core
         e = engine_ucc.get_energy(params, self.hamiltonian, self.n_qubits, self.n_elec, self.ex_ops, self.param_ids, self.hcb, self.init_state)
         return float(e) + self.e_core
 
@@ -180,6 +201,9 @@ class UCC:
         self._sanity_check()
         params = self._check_params_argument(params)
         self._check_engine(engine)
+        if self._sharded is not None:
+            e, g = self._sharded.energy_and_grad(params)
+            return float(e + self.e_core), np.asarray(g)
         e, g = engine_ucc.get_energy_and_grad(
             params, self.hamiltonian, self.n_qubits, self.n_elec, self.ex_ops, self.param_ids, self.hcb, self.init_state
         )

@@ -589,3 +589,22 @@ def test_sigma_by_row_blocks_sums_to_h_c():
     plan.from_storage_order_dev(sig_sto, out)
     torch.cuda.synchronize()
     assert (out - sig_ref).abs().max().item() < 1e-12
+
+
+def test_ucc_class_on_sharded_engine_kernel():
+    """UCCSD.shard(comm): the reference-shaped class API (energy, energy_and_grad, kernel) on the sharded engine gives
+    the same optimum as the single-GPU engine."""
+    from tencirchem_b200.sharded import LocalComm
+
+    ucc1, int1e, int2e = _build("uccsd", 3, 3)
+    e1 = ucc1.kernel()
+    ucc4 = UCCSD.from_integral(int1e, int2e, 6).shard(LocalComm(4))
+    e4 = ucc4.kernel()
+    assert abs(e1 - e4) < 1e-8
+    params = _params(ucc1.n_params)
+    ea, ga = ucc1.energy_and_grad(params)
+    eb, gb = ucc4.energy_and_grad(params)
+    assert abs(ea - eb) < E_TOL and np.abs(ga - gb).max() < G_TOL
+    assert np.abs(ucc1.civector(params) - ucc4.civector(params)).max() < C_TOL
+    with pytest.raises(ValueError):
+        PUCCD.from_integral(int1e, int2e, 6).shard(LocalComm(2))

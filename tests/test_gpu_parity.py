@@ -597,14 +597,17 @@ def test_ucc_class_on_sharded_engine_kernel():
     from tencirchem_b200.sharded import LocalComm
 
     ucc1, int1e, int2e = _build("uccsd", 3, 3)
-    e1 = ucc1.kernel()
     ucc4 = UCCSD.from_integral(int1e, int2e, 6).shard(LocalComm(4))
-    e4 = ucc4.kernel()
-    assert abs(e1 - e4) < 1e-8
     params = _params(ucc1.n_params)
     ea, ga = ucc1.energy_and_grad(params)
     eb, gb = ucc4.energy_and_grad(params)
-    assert abs(ea - eb) < E_TOL and np.abs(ga - gb).max() < G_TOL
+    assert abs(ea - eb) < E_TOL and np.abs(ga - gb).max() < G_TOL, (ea, eb)
+    assert abs(ucc1.energy(params) - ucc4.energy(params)) < E_TOL
     assert np.abs(ucc1.civector(params) - ucc4.civector(params)).max() < C_TOL
+    # L-BFGS-B on both engines: the same optimum up to the optimiser's own stopping tolerance
+    e1 = ucc1.kernel()
+    e4 = ucc4.kernel()
+    assert abs(e1 - e4) < 1e-6, (e1, e4)
+    assert np.abs(ucc4.energy_and_grad(ucc4.params)[1]).max() < 1e-3
     with pytest.raises(ValueError):
         PUCCD.from_integral(int1e, int2e, 6).shard(LocalComm(2))

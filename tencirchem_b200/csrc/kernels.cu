@@ -420,32 +420,56 @@ __global__ void sigma_ab_kernel(const double* __restrict__ c, double* __restrict
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
     const int mt_count = aml >> 3;
-    const int units = mt_count * (SAB_T / 16);
+    // unit of work of a warp: two 8-row tiles of G x 16 columns; the A fragments (rows of W) serve two column tiles and
+    // the B fragments (columns of D) two row tiles: one load per DMMA instead of 1.5
+    const int mp_count = (mt_count + 1) >> 1;
+    const int units = mp_count * (SAB_T / 16);
     const int g = lane >> 2, q4 = lane & 3;
     for (int u = warp; u < units; u += nwarps) {
-        int mt = u / (SAB_T / 16), nh = u - mt * (SAB_T / 16);
-        Link rl = alinks[a * aml + mt * 8 + g];
-        const double* wrow = w + int64_t(rl.pq) * n2p + q4;
+        const int mp = u / (SAB_T / 16), nh = u - mp * (SAB_T / 16);
+        const int mt0 = mp * 2, mt1 = mp * 2 + 1;
+        const bool two = mt1 < mt_count;
+        const Link rl0 = alinks[a * aml + mt0 * 8 + g];
+        Link rl1 = rl0;
+        if (two) rl1 = alinks[a * aml + mt1 * 8 + g];
+        const double* wrow0 = w + int64_t(rl0.pq) * n2p + q4;
+        const double* wrow1 = w + int64_t(rl1.pq) * n2p + q4;
         const double* dcol = dsm + q4 * SAB_LD + nh * 16 + g;
-        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double acc0[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, acc1[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        if (two) {
 #pragma unroll 4
-        for (int k0 = 0; k0 < n2p; k0 += 4) {
-            double av = __ldg(wrow + k0);
-            double bv0 = dcol[k0 * SAB_LD];
-            double bv1 = dcol[k0 * SAB_LD + 8];
-            dmma_m8n8k4(acc[0][0], acc[0][1], av, bv0);
-            dmma_m8n8k4(acc[1][0], acc[1][1], av, bv1);
+            for (int k0 = 0; k0 < n2p; k0 += 4) {
+                const double av0 = __ldg(wrow0 + k0), av1 = __ldg(wrow1 + k0);
+                const double bv0 = dcol[k0 * SAB_LD];
+                const double bv1 = dcol[k0 * SAB_LD + 8];
+                dmma_m8n8k4(acc0[0][0], acc0[0][1], av0, bv0);
+                dmma_m8n8k4(acc0[1][0], acc0[1][1], av0, bv1);
+                dmma_m8n8k4(acc1[0][0], acc1[0][1], av1, bv0);
+                dmma_m8n8k4(acc1[1][0], acc1[1][1], av1, bv1);
+            }
+        } else {
+#pragma unroll 4
+            for (int k0 = 0; k0 < n2p; k0 += 4) {
+                const double av0 = __ldg(wrow0 + k0);
+                const double bv0 = dcol[k0 * SAB_LD];
+                const double bv1 = dcol[k0 * SAB_LD + 8];
+                dmma_m8n8k4(acc0[0][0], acc0[0][1], av0, bv0);
+                dmma_m8n8k4(acc0[1][0], acc0[1][1], av0, bv1);
+            }
         }
-        if (rl.sgn != 0) {
-            double sg = double(rl.sgn);
+        auto scatter = [&](const Link& rl, double (&acc)[2][2]) {
+            if (rl.sgn == 0) return;
+            const double sg = double(rl.sgn);
             double* srow = sigma + int64_t(rl.addr) * nb;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                int64_t col = b0 + nh * 16 + nt * 8 + q4 * 2;
+                const int64_t col = b0 + nh * 16 + nt * 8 + q4 * 2;
                 if (col < nb) atomicAdd(srow + col, sg * acc[nt][0]);
                 if (col + 1 < nb) atomicAdd(srow + col + 1, sg * acc[nt][1]);
             }
-        }
+        };
+        scatter(rl0, acc0);
+        if (two) scatter(rl1, acc1);
     }
 }
 
@@ -457,7 +481,7 @@ void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, con
         aml = ml;
     }
     if (aml <= 0) return;
-    int units = (aml / 8) * (SAB_T / 16);
+    int units = ((aml / 8 + 1) / 2) * (SAB_T / 16);
     int best_nw = 4;
     double best_eff = 0.0;
     for (int nw = 4; nw <= 16; ++nw) {
@@ -469,11 +493,8 @@ void launch_sigma_ab(const double* c, double* sigma, int64_t na, int64_t nb, con
         }
     }
     size_t smem = size_t(n2p) * SAB_LD * sizeof(double);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(sigma_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        configured = smem;
-    }
+    // per device and cheap: no cached state (plans of several devices may live in one process)
+    if (smem > 48 * 1024) cudaFuncSetAttribute(sigma_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     // source rows [row_lo, row_lo + row_cnt) (default: all); their contributions go to every linked row of sigma
     const int64_t r_begin = row_cnt < 0 ? 0 : row_lo, gy_total = row_cnt < 0 ? na : row_lo + row_cnt;
     unsigned gx = unsigned((nb + SAB_T - 1) / SAB_T);

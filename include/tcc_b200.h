@@ -141,6 +141,13 @@ int64_t tcc_op_support_bytes(const tcc_plan* plan, int j);
 /* kernel launches issued by this plan since creation (for bench.py's gpu_launches) */
 int64_t tcc_launch_count(const tcc_plan* plan);
 
+/* ---- reduced density matrices (the immediate consumer of the CI vector) ------------------
+ * Replaces UCC.make_rdm1 / make_rdm2 in the MO basis (ucc.py:755-852), which copy the CI vector to the host and call
+ * pyscf direct_spin1.make_rdm1 / make_rdm12.  c_dev: reference-order CI vector on the device.  Spin-traced:
+ * rdm1[p,q] = <q+ p> ([n, n]); rdm2[p,q,r,s] = <p+ r+ s q> ([n, n, n, n], chemists' order, so that
+ * E = sum h1[p,q] rdm1[p,q] + 1/2 sum (pq|rs) rdm2[p,q,r,s]).  Either output may be NULL.  Not for hcb plans. */
+int tcc_make_rdm12(tcc_plan* plan, const double* c_dev, double* rdm1_host, double* rdm2_host, void* stream);
+
 /* ---- multi-GPU: alpha-row sharded plans -----------------------------
  * The [na, nb] CI matrix is split by alpha rows over `world` ranks (one process per GPU, world a power of
  * two).  A rank owns the rows whose occupation pattern on `t = log2(world)` alpha orbitals T equals its rank;

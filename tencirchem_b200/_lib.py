@@ -57,6 +57,7 @@ SIGNATURES = {
     "tcc_reverse_step": (C.c_int, [_p, C.c_int, C.c_double, _p, _p, _p, _p]),
     "tcc_op_support_bytes": (C.c_int64, [_p, C.c_int]),
     "tcc_launch_count": (C.c_int64, [_p]),
+    "tcc_make_rdm12": (C.c_int, [_p, _p, _dp, _dp, _p]),
     "tcc_plan_create_sharded": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
     "tcc_shard_info": (C.c_int, [_p, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
     "tcc_shard_segment": (C.c_int, [_p, C.c_int, _ip, _ip, _ip]),

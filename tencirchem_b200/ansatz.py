@@ -231,6 +231,36 @@ class UCC:
         self._check_engine(engine)
         return engine_ucc.apply_excitation(state, self.n_qubits, self.n_elec, ex_op, hcb=self.hcb)
 
+    # ---- reduced density matrices (ucc.py:755-852), MO basis of the integrals the ansatz was built from ----
+    def _rdm12(self, statevector=None):
+        import torch
+
+        from .evolve_civector import default_device, get_plan
+
+        if self.hcb:
+            raise AssertionError("RDMs are defined for the fermionic CI vector (ucc.py:786 asserts `not self.hcb`)")
+        civector = self.civector() if statevector is None else np.asarray(statevector, dtype=np.float64)
+        if len(civector) == self.statevector_size and self.statevector_size != self.civector_size:
+            civector = civector[self.get_ci_strings()]  # ucc.py:743-745
+        if len(civector) != self.civector_size:
+            raise ValueError(f"Incompatible statevector size: {len(civector)}")
+        plan = get_plan(self.n_qubits, self.n_elec, self.ex_ops or (), self.param_ids or (), self.hcb)
+        c_dev = torch.as_tensor(np.ascontiguousarray(civector), dtype=torch.float64, device=torch.device("cuda", default_device()))
+        return plan.make_rdm12_dev(c_dev)
+
+    def make_rdm1(self, statevector=None, basis: str = "MO") -> np.ndarray:
+        """Spin-traced 1RDM, rdm1[p,q] = <p_a^+ q_a> + <p_b^+ q_b> (ucc.py:755-797), computed on the GPU.  Only the MO
+        basis of the supplied integrals exists here (the reference's default "AO" needs its PySCF mean-field object)."""
+        if basis != "MO":
+            raise ValueError("this build works from MO integrals: only basis='MO' is available")
+        return self._rdm12(statevector)[0]
+
+    def make_rdm2(self, statevector=None, basis: str = "MO") -> np.ndarray:
+        """Spin-traced 2RDM in PySCF's convention rdm2[p,q,r,s] = <p^+ r^+ s q> (ucc.py:799-852), on the GPU."""
+        if basis != "MO":
+            raise ValueError("this build works from MO integrals: only basis='MO' is available")
+        return self._rdm12(statevector)[1]
+
     @property
     def e_ucc(self) -> float:
         """ucc.py:1033-1038."""

@@ -1099,6 +1099,67 @@ int tcc_apply_excitation(tcc_plan* p, const double* c_dev, const int32_t* ex_op,
     return 0;
 }
 
+// ---- reduced density matrices (ucc.py:755-852 -> pyscf direct_spin1.make_rdm1 / make_rdm12) ----------------------
+// rdm1[p,q] = <q+ p> and rdm2[p,q,r,s] = <p+ r+ s q>, spin-traced, of a reference-order CI vector on the device.
+int tcc_make_rdm12(tcc_plan* p, const double* c_dev, double* rdm1_host, double* rdm2_host, void* stream) {
+    if (!p || !c_dev || (!rdm1_host && !rdm2_host)) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
+    HostPlan& hp = p->hp;
+    if (hp.hcb) return fail(TCC_ERR_BAD_ARGUMENT, "RDMs are defined for the fermionic (non-hcb) CI vector only (ucc.py:786)");
+    cudaStream_t st = cudaStream_t(stream);
+    if (hp.links.empty()) hp.build_links();
+    if (!p->d_links) {
+        CUDA_TRY(dev_alloc(p, &p->d_links, hp.links.size()));
+        CUDA_TRY(cudaMemcpy(p->d_links, hp.links.data(), hp.links.size() * sizeof(Link), cudaMemcpyHostToDevice));
+    }
+    const double* src = c_dev;
+    if (!hp.identity_layout) {
+        if (int rc = ensure_vec(p, &p->ket)) return rc;
+        to_storage(p, c_dev, p->ket, st);
+        src = p->ket;
+    }
+    const int n = hp.n, n2 = n * n;
+    double* d_gram = nullptr;
+    CUDA_TRY(cudaMalloc(&d_gram, sizeof(double) * size_t(n2) * n2));
+    CUDA_TRY(cudaMemsetAsync(d_gram, 0, sizeof(double) * size_t(n2) * n2, st));
+    const int n_blocks = (n2 + 63) / 64, pairs = n_blocks * (n_blocks + 1) / 2;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, p->device));
+    const int slices = std::max(1, 4 * prop.multiProcessorCount / pairs);
+    launch_rdm_gram(src, hp.na, hp.nb, p->d_links, hp.ml, n, d_gram, slices, st);
+    p->launches += 1;
+    std::vector<double> gram(size_t(n2) * n2);
+    cudaError_t ce = cudaMemcpyAsync(gram.data(), d_gram, sizeof(double) * gram.size(), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(d_gram);
+    if (ce != cudaSuccess) return fail(TCC_ERR_CUDA, cudaGetErrorString(ce));
+    CUDA_TRY(cudaGetLastError());
+    // the kernel fills the 64 x 64 blocks I <= J: mirror the rest (the Gram matrix is symmetric)
+    for (int i = 0; i < n2; ++i)
+        for (int j = 0; j < i; ++j)
+            if ((i >> 6) > (j >> 6)) gram[size_t(i) * n2 + j] = gram[size_t(j) * n2 + i];
+    // <E_ps> = sum_q <E_ps E_qq> / n_elec = sum_q Gram[(s,p), (q,q)] / n_elec
+    std::vector<double> e1(n2, 0.0);
+    for (int pp = 0; pp < n; ++pp)
+        for (int ss = 0; ss < n; ++ss) {
+            double acc = 0.0;
+            for (int q = 0; q < n; ++q) acc += gram[size_t(ss * n + pp) * n2 + q * n + q];
+            e1[pp * n + ss] = hp.n_elec > 0 ? acc / double(hp.n_elec) : 0.0;
+        }
+    if (rdm1_host)
+        for (int pp = 0; pp < n; ++pp)
+            for (int q = 0; q < n; ++q) rdm1_host[pp * n + q] = e1[q * n + pp];  // dm1[p,q] = <q+ p>
+    if (rdm2_host)
+        for (int pp = 0; pp < n; ++pp)
+            for (int q = 0; q < n; ++q)
+                for (int r = 0; r < n; ++r)
+                    for (int ss = 0; ss < n; ++ss)
+                        rdm2_host[((size_t(pp) * n + q) * n + r) * n + ss] =
+                            gram[size_t(q * n + pp) * n2 + r * n + ss] - (q == r ? e1[pp * n + ss] : 0.0);
+    return 0;
+}
+
 int tcc_profile_enable(tcc_plan* p, int on) {
     if (!p) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     p->prof.on = on != 0;

@@ -47,4 +47,9 @@ void launch_sigma_hcb(const double* c, double* sigma, int64_t nstr, const uint32
                       const double* diag1, const double* hop, const double* diag2, const int64_t* binom,
                       int binom_ld, const int* bitpos, int n_sets, cudaStream_t st);
 
+// Gram matrix of the single-replacement intermediate D (rdm_kernels.cu); gram [n^2, n^2] must be zeroed; only the
+// blocks I <= J of the 64 x 64 block grid are written
+void launch_rdm_gram(const double* c, int64_t na, int64_t nb, const Link* links, int ml, int n, double* gram, int slices,
+                     cudaStream_t st);
+
 }  // namespace tcc

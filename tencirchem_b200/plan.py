@@ -173,6 +173,15 @@ class Plan:
         _lib.check(self.lib.tcc_shard_sigma_ab(self.handle, int(pass_id), self._ptr(c_local), self._ptr(sigma_local),
                                                self._stream()))
 
+    def make_rdm12_dev(self, c):
+        """(rdm1 [n, n], rdm2 [n, n, n, n]) of a reference-order CI vector on the device (tcc_make_rdm12)."""
+        self._check_dev(c, "c")
+        n = self.n_qubits // 2
+        rdm1 = np.zeros((n, n), dtype=np.float64)
+        rdm2 = np.zeros((n, n, n, n), dtype=np.float64)
+        _lib.check(self.lib.tcc_make_rdm12(self.handle, self._ptr(c), _dptr(rdm1), _dptr(rdm2), self._stream()))
+        return rdm1, rdm2
+
     def to_storage_order_dev(self, ref, out):
         """out (storage order) <- ref (reference order); full CI vectors on the device."""
         _lib.check(self.lib.tcc_to_storage_order(self.handle, self._ptr(ref), self._ptr(out), self._stream()))

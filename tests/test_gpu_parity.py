@@ -611,3 +611,30 @@ def test_ucc_class_on_sharded_engine_kernel():
     assert np.abs(ucc4.energy_and_grad(ucc4.params)[1]).max() < 1e-3
     with pytest.raises(ValueError):
         PUCCD.from_integral(int1e, int2e, 6).shard(LocalComm(2))
+
+
+@pytest.mark.parametrize("no,nv", [(1, 1), (2, 2), (2, 3), (3, 3), (4, 5)])
+def test_rdm12_on_gpu_against_oracle(no, nv):
+    """tcc_make_rdm12 (Gram matrix of the single-replacement intermediate on the FP64 tensor path) against the CPU
+    restatement of PySCF's conventions, plus the reference's own identity E = h.rdm1 + 1/2 eri.rdm2 (ucc.py:838-846)
+    through the class API.  (4e... ,9 orbitals) has n^2 = 81 > 64: two row blocks of the Gram matrix."""
+    from oracle import rdm_numpy as R
+
+    ucc, int1e, int2e = _build("uccsd", no, nv)
+    params = _params(ucc.n_params)
+    c = ucc.civector(params)
+    dm1_ref, dm2_ref = R.make_rdm12(c, no + nv, 2 * no)
+    dm1 = ucc.make_rdm1(c)
+    dm2 = ucc.make_rdm2(c)
+    assert np.abs(dm1 - dm1_ref).max() < 1e-12
+    assert np.abs(dm2 - dm2_ref).max() < 1e-12
+    e = np.einsum("pq,pq", int1e, dm1) + 0.5 * np.einsum("pqrs,pqrs", int2e, dm2)
+    assert abs(e - ucc.energy(params)) < E_TOL
+    # a non-normalised, non-symmetric random vector too
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal(ucc.civector_size)
+    a1, a2 = R.make_rdm12(v, no + nv, 2 * no)
+    assert np.abs(ucc.make_rdm1(v) - a1).max() < 1e-13 * np.abs(a1).max()  # |v|^2 ~ N: relative tolerance
+    assert np.abs(ucc.make_rdm2(v) - a2).max() < 1e-13 * np.abs(a2).max()
+    with pytest.raises(ValueError):
+        ucc.make_rdm1(c, basis="AO")

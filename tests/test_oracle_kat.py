@@ -240,3 +240,33 @@ def test_h4_adapt_vqe_pool_gradients_published():
         grads[str(ops_)] = g
     singles = [2 * sum(bra @ O.apply_excitation(psi, 8, 4, op, False) for op in grp) for grp in ([(6, 4), (2, 0)], [(7, 5), (3, 1)], [(7, 4), (3, 0)], [(6, 5), (2, 1)])]
     assert abs(np.linalg.norm(list(grads.values()) + singles) - k["h4_adapt_iter0_norm"]) < 2e-7
+
+
+def test_rdm_oracle_against_bruteforce_and_energy_identity():
+    """oracle/rdm_numpy.py (PySCF direct_spin1.make_rdm12 conventions used by ucc.py:755-852): element-wise against
+    brute-force ladder operators, plus the identity of the reference's own docstring example (ucc.py:838-846)."""
+    from oracle import bruteforce as bf
+    from oracle import rdm_numpy as R
+
+    n, ne = 3, 4
+    int1e, int2e = O.random_integral(n)
+    ns = len(O.make_strings(n, ne // 2))
+    rng = np.random.default_rng(11)
+    c = rng.standard_normal(ns * ns)
+    c /= np.linalg.norm(c)
+    dm1, dm2 = R.make_rdm12(c, n, ne)
+    dets = bf.basis(2 * n, ne)
+    assert len(dets) == ns * ns
+    for p in range(n):
+        for q in range(n):
+            words = [([(off + q, True), (off + p, False)], 1.0) for off in (0, n)]
+            assert abs(c @ bf.dense_from_words(dets, words) @ c - dm1[p, q]) < 1e-12
+            for r in range(n):
+                for s in range(n):
+                    words = [([(o1 + p, True), (o2 + r, True), (o2 + s, False), (o1 + q, False)], 1.0)
+                             for o1 in (0, n) for o2 in (0, n)]
+                    assert abs(c @ bf.dense_from_words(dets, words) @ c - dm2[p, q, r, s]) < 1e-12
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, ne)
+    e = np.einsum("pq,pq", int1e, dm1) + 0.5 * np.einsum("pqrs,pqrs", int2e, dm2)
+    assert abs(e - c @ h(c)) < 1e-12
+    assert abs(np.trace(dm1) - ne) < 1e-12

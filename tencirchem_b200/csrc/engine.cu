@@ -1336,14 +1336,19 @@ int tcc_shard_sigma_bb(tcc_plan* p, const double* c_local_dev, double* sigma_loc
     HostPlan& hp = p->hp;
     if (rows == 0) return 0;
     cudaStream_t st = cudaStream_t(stream);
-    if (int rc = ensure_rows_ws(p, size_t(rows) * size_t(hp.nb))) return rc;
+    // row chunks: the two transposed scratch blocks stay below ~2 GB each whatever the shard size
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(rows, int64_t(env_int("TCC_B200_BB_CHUNK_MB", 2048)) * (1 << 17) / hp.nb));
+    if (int rc = ensure_rows_ws(p, size_t(chunk) * size_t(hp.nb))) return rc;
     p->prof.mark(TCC_PROF_SIGMA_SS, st);
-    launch_transpose(c_local_dev, p->rows_ws1, rows, hp.nb, false, 1, st);
-    launch_spmm_rows(p->rows_ws1, p->rows_ws2, hp.nb, rows, p->d_ell_col, p->d_ell_val, hp.ell_width, false, 1, st);
-    launch_transpose(p->rows_ws2, sigma_local_dev, hp.nb, rows, true, 1, st);
-    p->prof.count(TCC_PROF_SIGMA_SS, 3, 7 * 8 * rows * hp.nb);
+    for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+        const int64_t nr = std::min(chunk, rows - r0);
+        launch_transpose(c_local_dev + r0 * hp.nb, p->rows_ws1, nr, hp.nb, false, 1, st);
+        launch_spmm_rows(p->rows_ws1, p->rows_ws2, hp.nb, nr, p->d_ell_col, p->d_ell_val, hp.ell_width, false, 1, st);
+        launch_transpose(p->rows_ws2, sigma_local_dev + r0 * hp.nb, hp.nb, nr, true, 1, st);
+        p->launches += 3;
+    }
+    p->prof.count(TCC_PROF_SIGMA_SS, 3 * ((rows + chunk - 1) / chunk), 7 * 8 * rows * hp.nb);
     p->prof.mark(-1, st);
-    p->launches += 3;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

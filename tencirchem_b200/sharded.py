@@ -383,7 +383,7 @@ class ShardedUCC:
             self.comm.all_reduce_sum(s_full)
             bras = [sig.index_select(0, self.mover.rows_dev(layout, st.rank)) for st, sig in zip(self.states, s_full)]
             del s_full
-        parts = [(bra * ket).sum().reshape(1) for bra, ket in zip(bras, kets)]
+        parts = [t.dot(bra.reshape(-1), ket.reshape(-1)).reshape(1) for bra, ket in zip(bras, kets)]  # no temporary
         self.comm.all_reduce_sum(parts)
         energy = float(parts[0][0])
         if not want_grad:

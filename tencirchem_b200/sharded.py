@@ -325,34 +325,44 @@ class ShardedUCC:
             if ket.numel():
                 st.plan.shard_sigma_bb(ket, s_loc)
             sig.append(s_loc)
-        # alpha-beta: pass i in layout l3[i]
+        # alpha-beta: pass i in layout l3[i].  The passes live in helper methods: a tensor that a loop variable of this
+        # frame still names would stay allocated through the next pass (a fifth shard at (20e,20o) is an OOM).
         for i, l in enumerate(l3):
-            c_i = self._reshard(kets, layout, l)
-            part = []
-            for st, c in zip(self.states, c_i):
-                s_i = t.zeros_like(c)
-                if c.numel():
-                    st.plan.shard_sigma_ab(i, c, s_i)
-                part.append(s_i)
-            del c_i
-            part = self._reshard(part, l, layout)
-            for s_loc, s_i in zip(sig, part):
-                s_loc += s_i
-            del part
+            self._sigma_ab_pass(i, l, kets, layout, sig)
         # alpha-alpha: on column blocks of all rows (in pieces, so that the transposed copies stay small)
         pieces = self.mover.column_pieces(layout)
         for j in range(pieces):
-            cols = self.mover.to_columns(kets, layout, j, pieces)
-            s_cols = []
-            for st, c in zip(self.states, cols):
-                out = t.empty_like(c)
-                if c.numel():
-                    st.plan.shard_sigma_aa(c, out)
-                s_cols.append(out)
-            del cols
-            self.mover.to_rows(s_cols, layout, j, pieces, add_into=sig)
-            del s_cols
+            self._sigma_aa_piece(j, pieces, kets, layout, sig)
         return sig
+
+    def _sigma_ab_pass(self, i, l, kets, layout, sig):
+        """sig += pass i of the opposite-spin terms.  Peak: kets + sig + the moved copy + its partial sigma."""
+        t = self.torch
+        c_i = self._reshard(kets, layout, l)
+        part = []
+        for k in range(len(self.states)):
+            s_i = t.zeros_like(c_i[k])
+            if s_i.numel():
+                self.states[k].plan.shard_sigma_ab(i, c_i[k], s_i)
+            part.append(s_i)
+            del s_i
+        del c_i
+        part = self._reshard(part, l, layout)
+        for k in range(len(sig)):
+            sig[k] += part[k]
+
+    def _sigma_aa_piece(self, j, pieces, kets, layout, sig):
+        t = self.torch
+        cols = self.mover.to_columns(kets, layout, j, pieces)
+        s_cols = []
+        for k in range(len(self.states)):
+            out = t.empty_like(cols[k])
+            if out.numel():
+                self.states[k].plan.shard_sigma_aa(cols[k], out)
+            s_cols.append(out)
+            del out
+        del cols
+        self.mover.to_rows(s_cols, layout, j, pieces, add_into=sig)
 
     def civector(self, params) -> np.ndarray:
         """Reference-order CI vector on the host (small systems / tests: gathers the full vector)."""

@@ -667,3 +667,33 @@ def test_sharded_full_size_16o_matches_single_gpu():
         assert eng.reshards > 0
         del eng
         torch.cuda.empty_cache()
+
+
+def test_sharded_distributed_sigma_peak_memory():
+    """The distributed H c must peak at ket + sigma + one moved copy + its partial (4 shards per rank, plus bounded
+    staging): a fifth live shard is an out-of-memory error at (20e,20o) on 8 GPUs (35.9 GB shards, 180 GB HBM)."""
+    import torch
+
+    from tencirchem_b200.sharded import LocalComm, ShardedUCC
+
+    n, world = 12, 2
+    int1e, int2e = random_integral(n)
+    ucc = UCCSD.from_integral(int1e, int2e, n)
+    ex_ops, param_ids = ucc.ex_ops[:40], list(range(40))
+    eng = ShardedUCC(2 * n, n, ex_ops, param_ids, LocalComm(world), sigma_mode="distributed", chunk_bytes=256 << 10)
+    eng.set_hamiltonian(int1e, int2e)
+    params = 0.1 * _params(40)
+    kets, layout = eng._forward(params)
+    shard = max(k.numel() for k in kets) * 8
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    torch.cuda.reset_peak_memory_stats()
+    bras = eng._sigma_distributed(kets, layout)
+    torch.cuda.synchronize()
+    extra = torch.cuda.max_memory_allocated() - base  # beyond the kets, for both virtual ranks
+    assert extra < world * 3.4 * shard, (extra / shard, "shards beyond the kets")
+    # and the result is H c: compare with the replicated mode
+    eng2 = ShardedUCC(2 * n, n, ex_ops, param_ids, LocalComm(world), sigma_mode="replicated")
+    eng2.set_hamiltonian(int1e, int2e)
+    e1 = sum(float(torch.dot(b.reshape(-1), k.reshape(-1))) for b, k in zip(bras, kets))
+    assert abs(e1 - eng2.energy(params)) < E_TOL

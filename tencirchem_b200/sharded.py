@@ -294,13 +294,14 @@ class ShardedUCC:
             if pos < len(rows) and rows[pos] == self.hf_row:
                 ket[pos, self.hf_row] = 1.0
             kets.append(ket)
+            del ket
         layout = first
         for seg, (l, _, _) in enumerate(self.segments):
             kets = self._reshard(kets, layout, l)
             layout = l
-            for st, ket in zip(self.states, kets):
-                if ket.numel():  # a rank may own no row in a layout of a tiny active space
-                    st.plan.shard_forward(seg, ket)
+            for k, st in enumerate(self.states):
+                if kets[k].numel():  # a rank may own no row in a layout of a tiny active space
+                    st.plan.shard_forward(seg, kets[k])
         return kets, layout
 
     def _gather_full(self, vecs, layout):
@@ -334,6 +335,22 @@ class ShardedUCC:
         for j in range(pieces):
             self._sigma_aa_piece(j, pieces, kets, layout, sig)
         return sig
+
+    def _sigma_replicated(self, kets, layout):
+        """sigma = H c on the all-reduced full vector: every rank contracts a block of rows, the blocks are summed and
+        each rank keeps its rows.  Two full vectors per GPU."""
+        t = self.torch
+        c_full = self._gather_full(kets, layout)
+        s_full = []
+        for k, st in enumerate(self.states):
+            sig = t.zeros_like(c_full[k])
+            lo, hi = shard_bounds(self.na, st.rank, self.world)
+            st.plan.apply_h_rows(c_full[k], sig, lo, hi - lo)
+            s_full.append(sig)
+            del sig
+        del c_full
+        self.comm.all_reduce_sum(s_full)
+        return [s_full[k].index_select(0, self.mover.rows_dev(layout, st.rank)) for k, st in enumerate(self.states)]
 
     def _sigma_ab_pass(self, i, l, kets, layout, sig):
         """sig += pass i of the opposite-spin terms.  Peak: kets + sig + the moved copy + its partial sigma."""
@@ -381,18 +398,7 @@ class ShardedUCC:
         if self.sigma_mode == "distributed":
             bras = self._sigma_distributed(kets, layout)
         else:
-            # sigma = H c: every rank contracts a block of rows of the gathered vector; the blocks are summed
-            c_full = self._gather_full(kets, layout)
-            s_full = []
-            for st, c in zip(self.states, c_full):
-                sig = t.zeros_like(c)
-                lo, hi = shard_bounds(self.na, st.rank, self.world)
-                st.plan.apply_h_rows(c, sig, lo, hi - lo)
-                s_full.append(sig)
-            del c_full
-            self.comm.all_reduce_sum(s_full)
-            bras = [sig.index_select(0, self.mover.rows_dev(layout, st.rank)) for st, sig in zip(self.states, s_full)]
-            del s_full
+            bras = self._sigma_replicated(kets, layout)
         parts = [t.dot(bra.reshape(-1), ket.reshape(-1)).reshape(1) for bra, ket in zip(bras, kets)]  # no temporary
         self.comm.all_reduce_sum(parts)
         energy = float(parts[0][0])
@@ -403,9 +409,9 @@ class ShardedUCC:
             kets = self._reshard(kets, layout, l)
             bras = self._reshard(bras, layout, l)
             layout = l
-            for st, ket, bra in zip(self.states, kets, bras):
-                if ket.numel():
-                    st.plan.shard_reverse(seg, ket, bra)
+            for k, st in enumerate(self.states):  # by index: no loop variable may keep a shard of the old layout alive
+                if kets[k].numel():
+                    st.plan.shard_reverse(seg, kets[k], bras[k])
         grads = [t.as_tensor(st.plan.shard_gradient(), dtype=t.float64, device=self.device) for st in self.states]
         self.comm.all_reduce_sum(grads)
         return energy, grads[0].cpu().numpy()

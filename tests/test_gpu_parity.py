@@ -604,11 +604,14 @@ def test_ucc_class_on_sharded_engine_kernel():
     assert abs(ea - eb) < E_TOL and np.abs(ga - gb).max() < G_TOL, (ea, eb)
     assert abs(ucc1.energy(params) - ucc4.energy(params)) < E_TOL
     assert np.abs(ucc1.civector(params) - ucc4.civector(params)).max() < C_TOL
-    # L-BFGS-B on both engines: the same optimum up to the optimiser's own stopping tolerance
-    e1 = ucc1.kernel()
+    # L-BFGS-B driven by the sharded engine: it converges, and the single-GPU engine agrees at the optimum (two
+    # optimiser runs are not compared with each other: rounding-level differences may end in different local minima)
+    e_start = ucc4.energy(np.zeros(ucc4.n_params))
     e4 = ucc4.kernel()
-    assert abs(e1 - e4) < 1e-6, (e1, e4)
-    assert np.abs(ucc4.energy_and_grad(ucc4.params)[1]).max() < 1e-3
+    assert e4 < e_start
+    e_opt, g_opt = ucc1.energy_and_grad(ucc4.params)
+    assert abs(e_opt - e4) < E_TOL
+    assert np.abs(g_opt).max() < 1e-3
     with pytest.raises(ValueError):
         PUCCD.from_integral(int1e, int2e, 6).shard(LocalComm(2))
 

@@ -270,3 +270,20 @@ def test_rdm_oracle_against_bruteforce_and_energy_identity():
     e = np.einsum("pq,pq", int1e, dm1) + 0.5 * np.einsum("pqrs,pqrs", int2e, dm2)
     assert abs(e - c @ h(c)) < 1e-12
     assert abs(np.trace(dm1) - ne) < 1e-12
+
+
+def test_rdm_oracle_reproduces_the_reference_docstring_example_h2():
+    """ucc.py:838-846 (make_rdm2 doctest): for the H2 HF state [1, 0, 0, 0],
+    int1e.rdm1 + 1/2 int2e.rdm2 + e_nuc equals the published HF energy."""
+    from oracle import rdm_numpy as R
+
+    k = KAT["h2_sto3g"]
+    int1e, int2e = h2_integrals()
+    rdm1, rdm2 = R.make_rdm12(np.array([1.0, 0.0, 0.0, 0.0]), 2, 2)
+    e_hf = int1e.ravel() @ rdm1.ravel() + 0.5 * int2e.ravel() @ rdm2.ravel()
+    assert abs(e_hf + k["e_nuc"] - k["e_hf"]) < 1e-10  # the doctest's own tolerance
+    # and at the published UCC optimum
+    c = np.array(k["civector"])
+    rdm1, rdm2 = R.make_rdm12(c, 2, 2)
+    e = int1e.ravel() @ rdm1.ravel() + 0.5 * int2e.ravel() @ rdm2.ravel()
+    assert abs(e + k["e_nuc"] - k["e_ucc"]) < 1e-8  # the published amplitudes carry 9 digits

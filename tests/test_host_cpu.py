@@ -145,3 +145,29 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".hpp", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` runs on the host cores (no GPU) and prints ONE JSON line with the contract's keys;
+    under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "4o", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "uccsd_energy_and_grad_evals_per_s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # a non-zero rank of a multi-rank launch exits 0 without output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""

@@ -170,6 +170,10 @@ int tcc_shard_set_params(tcc_plan* plan, const double* params_host, void* stream
 /* all batches of segment `seg` on the local rows (storage order, layout of the segment) */
 int tcc_shard_forward(tcc_plan* plan, int seg, double* vec_local_dev, void* stream);
 int tcc_shard_reverse(tcc_plan* plan, int seg, double* ket_local_dev, double* bra_local_dev, void* stream);
+/* the same with a row stride (in doubles): 2 * num_strings when ket and bra rows are interleaved in one
+ * [rows, 2, nb] block, so that a single row move between segments serves both vectors */
+int tcc_shard_reverse_strided(tcc_plan* plan, int seg, double* ket_local_dev, double* bra_local_dev,
+                              int64_t row_stride, void* stream);
 /* this rank's share of 2 * <bra|G_j|ket> summed by parameter; the caller adds the shares (all-reduce) */
 int tcc_shard_gradient(tcc_plan* plan, double* grad_host /* [num_params] */, void* stream);
 /* Contributions to sigma = H c of the storage rows [row_lo, row_lo + row_cnt): same-spin terms of these rows and

@@ -65,6 +65,7 @@ SIGNATURES = {
     "tcc_shard_set_params": (C.c_int, [_p, _dp, _p]),
     "tcc_shard_forward": (C.c_int, [_p, C.c_int, _p, _p]),
     "tcc_shard_reverse": (C.c_int, [_p, C.c_int, _p, _p, _p]),
+    "tcc_shard_reverse_strided": (C.c_int, [_p, C.c_int, _p, _p, C.c_int64, _p]),
     "tcc_shard_gradient": (C.c_int, [_p, _dp, _p]),
     "tcc_apply_h_rows": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, _p]),
     "tcc_shard_sigma_layouts": (C.c_int, [_p, _ip]),

@@ -1227,16 +1227,19 @@ int tcc_shard_forward(tcc_plan* p, int seg, double* vec_local_dev, void* stream)
     return 0;
 }
 
-int tcc_shard_reverse(tcc_plan* p, int seg, double* ket_local_dev, double* bra_local_dev, void* stream) {
+// row_stride: distance in doubles between consecutive local rows of ket (and of bra); nb for separate [rows, nb]
+// matrices, 2 nb when ket and bra rows are interleaved in one [rows, 2, nb] block (one row move serves both)
+int tcc_shard_reverse_strided(tcc_plan* p, int seg, double* ket_local_dev, double* bra_local_dev, int64_t row_stride, void* stream) {
     if (!p || !ket_local_dev || !bra_local_dev || seg < 0 || seg >= int(p->hp.segments.size()))
         return fail(TCC_ERR_BAD_ARGUMENT, "bad argument");
+    if (row_stride < p->hp.nb) return fail(TCC_ERR_BAD_ARGUMENT, "row stride smaller than a row");
     if (int rc_dev = use_device(p)) return rc_dev;
     cudaStream_t st = cudaStream_t(stream);
     const Segment& s = p->hp.segments[seg];
     p->prof.mark(TCC_PROF_REV_BATCH, st);
     for (int b = s.batch_hi - 1; b >= s.batch_lo; --b) {
         BatchDevSet& db = p->dbatches[b];
-        launch_batch_reverse(ket_local_dev, bra_local_dev, p->hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart,
+        launch_batch_reverse(ket_local_dev, bra_local_dev, row_stride, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart,
                              p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
         p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
         p->launches += 2;
@@ -1244,6 +1247,10 @@ int tcc_shard_reverse(tcc_plan* p, int seg, double* ket_local_dev, double* bra_l
     p->prof.mark(-1, st);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+int tcc_shard_reverse(tcc_plan* p, int seg, double* ket_local_dev, double* bra_local_dev, void* stream) {
+    return tcc_shard_reverse_strided(p, seg, ket_local_dev, bra_local_dev, p ? p->hp.nb : 0, stream);
 }
 
 // this rank's share of the gradient (sum over its tiles), by parameter, with the factor 2 of evolve_civector.py:218;

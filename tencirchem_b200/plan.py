@@ -146,6 +146,11 @@ class Plan:
         _lib.check(self.lib.tcc_shard_reverse(self.handle, int(seg), C.c_void_p(ket_local.data_ptr()),
                                               C.c_void_p(bra_local.data_ptr()), self._stream()))
 
+    def shard_reverse_strided(self, seg: int, ket_local, bra_local, row_stride: int):
+        """ket_local / bra_local: views whose consecutive rows lie `row_stride` doubles apart (interleaved block)."""
+        _lib.check(self.lib.tcc_shard_reverse_strided(self.handle, int(seg), C.c_void_p(ket_local.data_ptr()),
+                                                      C.c_void_p(bra_local.data_ptr()), int(row_stride), self._stream()))
+
     def shard_gradient(self) -> np.ndarray:
         g = np.zeros(max(self.n_params, 1), dtype=np.float64)
         _lib.check(self.lib.tcc_shard_gradient(self.handle, _dptr(g), self._stream()))

@@ -129,8 +129,8 @@ class RowMover:
             self._rows_dev[key] = t.as_tensor(self.rows[layout][rank], dtype=t.int64, device=self.device)
         return self._rows_dev[key]
 
-    def _move_plan(self, l_from: int, l_to: int, rank: int):
-        key = (l_from, l_to, rank)
+    def _move_plan(self, l_from: int, l_to: int, rank: int, row_elems: int):
+        key = (l_from, l_to, rank, row_elems)
         if key not in self._moves:
             t = self.torch
             mine_from = self.rows[l_from][rank]
@@ -138,7 +138,7 @@ class RowMover:
             n_max = max(max(len(r) for r in self.rows[l_from]), 1)
             # the move runs in `pieces` rounds so that the staging buffers stay below chunk_bytes (every rank derives
             # the same number of rounds and the same split of every (source, destination) row list)
-            pieces = max(1, -(-(n_max * self.nb * 8) // self.chunk_bytes))
+            pieces = max(1, -(-(n_max * row_elems * 8) // self.chunk_bytes))
             send_idx, recv_idx = [], []
             for peer in range(self.world):
                 out_rows = np.intersect1d(mine_from, self.rows[l_to][peer], assume_unique=True)
@@ -161,7 +161,8 @@ class RowMover:
         if l_from == l_to:
             return vecs
         self.reshards += 1
-        plans = [self._move_plan(l_from, l_to, r) for r in self.comm.local_ranks]
+        row_elems = int(vecs[0][0].numel()) if vecs[0].shape[0] else int(np.prod(vecs[0].shape[1:]))
+        plans = [self._move_plan(l_from, l_to, r, row_elems) for r in self.comm.local_ranks]
         out = [t.empty((mp[1],) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device) for v, mp in zip(vecs, plans)]
         for j in range(len(plans[0][0])):
             rnd = [mp[0][j] for mp in plans]
@@ -239,7 +240,8 @@ class _RankState:
 class ShardedUCC:
     """energy / energy_and_grad / civector of one ansatz with the CI vector sharded over `comm.world` ranks."""
 
-    def __init__(self, n_qubits, n_elec, ex_ops, param_ids, comm, device=0, sigma_mode="auto", chunk_bytes=4 << 30):
+    def __init__(self, n_qubits, n_elec, ex_ops, param_ids, comm, device=0, sigma_mode="auto", chunk_bytes=4 << 30,
+                 fuse_reverse_moves="auto"):
         """sigma_mode: "distributed" keeps the vector sharded through H c (three alpha-beta passes + a column
         transpose for the alpha-alpha terms); "replicated" all-reduces the full vector (2 full vectors per GPU; faster:
         one pass of the opposite-spin kernel); "auto" = replicated while two full vectors take less than a quarter of
@@ -256,6 +258,9 @@ class ShardedUCC:
             total = torch.cuda.get_device_properties(int(device)).total_memory
             sigma_mode = "replicated" if 2 * full_bytes < total // 4 else "distributed"
         self.sigma_mode = sigma_mode if comm.world > 1 else "replicated"
+        # reverse sweep: ket and bra rows interleaved in one [rows, 2, nb] block move with ONE all-to-all per segment
+        # instead of two; costs two extra shards while the block is built ("auto": only while that is < 1/8 of HBM)
+        self.fuse_reverse_moves = fuse_reverse_moves
         self.torch = torch
         self.comm = comm
         self.world = comm.world
@@ -404,14 +409,29 @@ class ShardedUCC:
         energy = float(parts[0][0])
         if not want_grad:
             return energy, None
-        for seg in range(len(self.segments) - 1, -1, -1):
-            l = self.segments[seg][0]
-            kets = self._reshard(kets, layout, l)
-            bras = self._reshard(bras, layout, l)
-            layout = l
-            for k, st in enumerate(self.states):  # by index: no loop variable may keep a shard of the old layout alive
-                if kets[k].numel():
-                    st.plan.shard_reverse(seg, kets[k], bras[k])
+        fuse = self.fuse_reverse_moves
+        if fuse == "auto":
+            total = t.cuda.get_device_properties(self.device).total_memory
+            fuse = self.world > 1 and 2 * 8 * max(k_.numel() for k_ in kets) < total // 8
+        if fuse:
+            both = [t.stack((kets[k], bras[k]), dim=1) for k in range(len(kets))]  # [rows, 2, nb]
+            del kets, bras
+            for seg in range(len(self.segments) - 1, -1, -1):
+                l = self.segments[seg][0]
+                both = self._reshard(both, layout, l)
+                layout = l
+                for k, st in enumerate(self.states):
+                    if both[k].numel():
+                        st.plan.shard_reverse_strided(seg, both[k][:, 0], both[k][:, 1], 2 * self.nb)
+        else:
+            for seg in range(len(self.segments) - 1, -1, -1):
+                l = self.segments[seg][0]
+                kets = self._reshard(kets, layout, l)
+                bras = self._reshard(bras, layout, l)
+                layout = l
+                for k, st in enumerate(self.states):  # by index: no loop variable keeps a shard of the old layout alive
+                    if kets[k].numel():
+                        st.plan.shard_reverse(seg, kets[k], bras[k])
         grads = [t.as_tensor(st.plan.shard_gradient(), dtype=t.float64, device=self.device) for st in self.states]
         self.comm.all_reduce_sum(grads)
         return energy, grads[0].cpu().numpy()

@@ -556,7 +556,8 @@ def test_sharded_virtual_ranks_match_oracle(world, tile_elems, monkeypatch):
         for sigma_mode in (("distributed", "replicated") if world > 1 else ("replicated",)):
             # a small staging budget forces the row moves and the column transposes to run in several rounds
             eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, LocalComm(world), sigma_mode=sigma_mode,
-                             chunk_bytes=(4 << 30) if tile_elems == 6144 else 1024)
+                             chunk_bytes=(4 << 30) if tile_elems == 6144 else 1024,
+                             fuse_reverse_moves=(sigma_mode == "replicated"))
             eng.set_hamiltonian(int1e, int2e)
             assert np.abs(eng.civector(params) - c_ref).max() < C_TOL
             e, g = eng.energy_and_grad(params)
@@ -661,8 +662,9 @@ def test_sharded_full_size_16o_matches_single_gpu():
     del plan
     torch.cuda.empty_cache()
     for mode in ("replicated", "distributed"):
+        # the reverse sweep moves ket and bra separately in one run and as one interleaved block in the other
         eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, LocalComm(2), sigma_mode=mode,
-                         chunk_bytes=256 << 20)
+                         chunk_bytes=256 << 20, fuse_reverse_moves=(mode == "distributed"))
         eng.set_hamiltonian(int1e, int2e)
         e2, g2 = eng.energy_and_grad(params)
         assert abs(e1 - e2) < E_TOL, (mode, e1, e2)

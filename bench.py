@@ -9,8 +9,13 @@ Contract (one JSON line on stdout from rank 0):
 * default workload: (16e,16o), N = 165,636,900 determinants, M = 5792 excitations, P = 2928 parameters
   (BASELINE.json configs[3], the size its target is quoted on; a 1.3 GB vector >> the 126 MB L2, so no
   explicit L2 flush is needed between steps).
-* N > 1: every rank evaluates its own theta set (batched parameter sets shard trivially; no data-path
-  collective), `value` = all ranks' evaluations / max-over-ranks time, scaling "weak".
+* N > 1 (default `--multi sharded`): ONE evaluation at a time with the CI vector split by alpha rows over the N
+  ranks (tencirchem_b200/sharded.py; NCCL row moves between the row layouts of the batch segments), every rank
+  evaluates the same theta, `value` = evaluations / max-over-ranks device time, scaling "strong".
+  `--multi replicas` / `--batch B`: every rank evaluates its own theta sets (no data-path collective), scaling "weak".
+* `--parity-golden`: before the timed region the engine evaluates the committed sparse-oracle case of the workload
+  (tests/golden/sparse_parity_<n>o.json: full op list, sparse initial state, a few non-zero parameters) and the JSON
+  line carries the absolute errors (`parity`); it doubles as a warm-up evaluation.
 * `--impl reference`: the CPU oracle port of the reference numpy engine (oracle/civector_numpy.py; the
   Python reference itself cannot be imported here -- DESIGN.md) timed on a bounded sample, rank 0 only.
 """
@@ -174,30 +179,96 @@ def cpu_reference_sample(n, n_ops_sample=2, ansatz="uccsd"):
             "note": "numpy fancy-index gathers and elementwise passes are single-threaded, exactly as in the reference's numpy backend; the BLAS pool (all host cpus) is used only by the dgemm of H.c"}
 
 
+def scaling_label(args, world):
+    """the default N > 1 run shards ONE evaluation over the ranks (fixed total work): a strong-scaling curve, N = 1
+    included; replicas / batched theta sets per rank are weak scaling"""
+    sharded = args.multi == "sharded" and args.batch == 0 and args.ansatz != "puccd"
+    return "strong" if sharded else "weak"
+
+
+def workload_config(n, args):
+    """the workload keys both arms print (same inputs, same sizes)"""
+    from math import comb
+
+    from oracle import pools  # integer op-pool generators only (bench legs may import oracle/; the product never does)
+
+    no = n // 2
+    hcb = args.ansatz == "puccd"
+    ops, pids = {"uccsd": pools.uccsd_ex_ops, "kupccgsd": pools.kupccgsd_ex_ops, "puccd": pools.puccd_ex_ops}[args.ansatz](no, n - no)
+    if args.max_ops > 0:
+        ops, pids = ops[: args.max_ops], pids[: args.max_ops]
+    size = comb(n, no) if hcb else comb(n, no) ** 2
+    return {"workload": workload_desc(n, args.ansatz, args.integrals), "n_determinants": size, "n_excitations": len(ops),
+            "n_params": len(set(pids))}
+
+
 def run_reference(args):
+    """`--impl reference`: the CPU port of the reference's numpy engine on this box's host cores, rank 0 only.  One
+    full evaluation takes hours at (16e,16o), so a step is a bounded sample extrapolated by operation counts
+    (cpu_reference_sample); the sample is timed ONCE (after one smaller warm-up sample) and every step reports it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = WORKLOADS[args.workload]
-    res = None
-    times = []
-    for step in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        res = cpu_reference_sample(n, n_ops_sample=1 if step < args.warmup else 2, ansatz=args.ansatz)
-        if step >= args.warmup:
-            times.append(1.0 / res["value"])
-    t_eval = float(np.mean(times))
+    if args.warmup > 0:
+        cpu_reference_sample(n, n_ops_sample=1, ansatz=args.ansatz)
+    res = cpu_reference_sample(n, n_ops_sample=2, ansatz=args.ansatz)
+    t_eval = 1.0 / res["value"]
+    cfg = workload_config(n, args)
+    cfg["note"] = ("CPU oracle port of the reference numpy engine; the bounded sample is timed once and extrapolated by "
+                   "operation counts to one evaluation; every step reports that figure")
     line = {
         "impl": "reference", "metric": METRIC, "value": 1.0 / t_eval, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_eval, "higher_is_better": True,
-        "scaling": "strong" if args.gpus > 1 and args.multi == "sharded" and args.batch == 0 else "weak",
+        "scaling": scaling_label(args, args.gpus),
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(n, args.ansatz, args.integrals), "note": "CPU oracle port of the reference numpy engine; each step is a bounded sample extrapolated by operation counts"},
+        "config": cfg,
         "cpu_baseline": {**res, "value": 1.0 / t_eval},
         "e2e": {"value": 1.0 / t_eval, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def progress(msg):
+    """append a line to gpurun_out/bench_progress.log: a long multi-GPU run that dies leaves a trace of how far it got"""
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "bench_progress.log"), "a") as f:
+            f.write(f"{time.strftime('%H:%M:%S')} {msg}\n")
+    except OSError:
+        pass
+
+
+def golden_parity(n, evaluate, rank=0):
+    """Evaluates the committed sparse-oracle case of the workload (tests/golden/sparse_parity_<n>o.json) through
+    `evaluate(params, (alpha_ref_addr, beta_ref_addr, amps)) -> (energy, grad)` and returns the absolute errors."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_cases import SparseCase
+
+    case = SparseCase(n)
+    t0 = time.perf_counter()
+    e, g = evaluate(case.params, case.init_sparse())
+    res = case.check(e, g)
+    res.update({"case": f"tests/golden/sparse_parity_{n}o.json (sparse oracle, oracle/sparse.py)", "energy": e,
+                "energy_expected": case.energy, "seconds": round(time.perf_counter() - t0, 1)})
+    return res
+
+
+def driver_phase_table(summary, steps, step_ms):
+    """per-step device / host ms of the sharded driver's phases (ShardedUCC.timer), with the NVLink GB/s of the
+    collectives (bytes this rank sent, over the time the compute stream waited for the collective)"""
+    out = {}
+    for name, d in sorted(summary.items(), key=lambda kv: -kv[1]["device_ms"]):
+        row = {"device_ms_per_step": round(d["device_ms"] / steps, 3), "host_ms_per_step": round(d["host_ms"] / steps, 3),
+               "calls_per_step": d["calls"] // steps, "share_of_step": round(d["device_ms"] / steps / step_ms, 4) if step_ms else None}
+        if d["bytes"]:
+            row["GB_sent_per_step"] = round(d["bytes"] / steps / 1e9, 3)
+            row["GBps"] = round(d["bytes"] / (d["device_ms"] * 1e-3) / 1e9, 1) if d["device_ms"] > 0 else None
+        out[name] = row
+    covered = sum(d["device_ms"] for d in summary.values()) / steps
+    out["_unattributed_ms_per_step"] = round(step_ms - covered, 3)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -217,7 +288,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     torch.cuda.init()
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # keep NCCL's version banner off stdout unless the caller asked for it (the driver reads NCCL_DEBUG=INFO lines)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = WORKLOADS[args.workload]
@@ -260,6 +332,15 @@ def run_b200(args):
     if args.batch > 0:
         return run_b200_batched(args, plan, ucc, theta, barrier, world, rank, n, staging_s)
 
+    parity = None
+    if args.parity_golden:
+        def evaluate(p_, init):
+            ia, ib, iv = init
+            x = torch.zeros(plan.size, dtype=torch.float64, device="cuda")
+            x[torch.as_tensor(ia * plan.n_strings + ib, device="cuda")] = torch.as_tensor(iv, device="cuda")
+            return plan.energy_and_grad_dev(p_, init=x)
+
+        parity = golden_parity(n, evaluate, rank)
     for w in range(args.warmup):
         plan.energy_and_grad_dev(theta(-1 - w))
     barrier()
@@ -328,7 +409,8 @@ def run_b200(args):
     dense_bytes = (48 * m + 16) * size
     line = {
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak" if world > 1 else scaling_label(args, world), "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_desc(n, args.ansatz, args.integrals), "n_determinants": size, "n_excitations": m, "n_params": p_count,
                    "l2": "inputs larger than L2 (1.3 GB vectors vs 126 MB)" if size * 8 > 2.5e8 else "vectors fit in L2; no flush",
@@ -347,6 +429,8 @@ def run_b200(args):
         "clocks": clocks,
         "energy_last_step": last[0],
     }
+    if parity is not None:
+        line["parity"] = parity
     if not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_reference_sample(n, n_ops_sample=2, ansatz=args.ansatz)
@@ -370,7 +454,8 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
     torch.cuda.empty_cache()
     m, p_count, size = len(ucc.ex_ops), ucc.n_params, ucc.civector_size
     t0 = time.perf_counter()
-    eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, TorchComm(), device=local_rank, sigma_mode=args.sigma)
+    eng = ShardedUCC(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, TorchComm(), device=local_rank, sigma_mode=args.sigma,
+                     chunk_bytes=int(args.chunk_gib * 2**30))
     eng.set_hamiltonian(int1e, int2e)
     staging_s = time.perf_counter() - t0
     plan = eng.states[0].plan
@@ -383,10 +468,19 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
         dist.barrier()
         torch.cuda.synchronize()
 
+    progress(f"rank {rank}: plans + Hamiltonian ready after {staging_s:.1f} s, {torch.cuda.memory_allocated() / 2**30:.1f} GiB allocated by torch")
+    parity = None
+    if args.parity_golden:
+        parity = golden_parity(n, lambda p_, init: eng.energy_and_grad(p_, init_sparse=init), rank)
+        progress(f"rank {rank}: golden parity {parity}")
     for w in range(args.warmup):
         eng.energy_and_grad(theta(-1 - w))
+        progress(f"rank {rank}: warm-up {w} done")
     barrier()
     plan.profile_enable(True)
+    eng.timer.enabled = True
+    eng.timer.reset()
+    torch.cuda.reset_peak_memory_stats()
     launches0 = plan.launch_count
     reshards0 = eng.reshards
     sampler = ClockSampler(local_rank)
@@ -407,11 +501,16 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
     clocks = sampler.stop() if rank == 0 else None
     prof = plan.profile_read()
     plan.profile_enable(False)
+    driver_phases = eng.timer.summary()
+    eng.timer.enabled = False
     launches = plan.launch_count - launches0
     reshards = (eng.reshards - reshards0) // max(args.steps, 1)
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    peak_gib = torch.cuda.max_memory_allocated() / 2**30
+    free_b, total_b = torch.cuda.mem_get_info()
+    t = torch.tensor([dev_ms, e2e_s * 1e3, peak_gib, (total_b - free_b) / 2**30], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, peak_gib, used_gib = (float(x) for x in t)
+    progress(f"rank {rank}: {args.steps} timed step(s) done, {dev_ms / args.steps:.1f} ms per step (max over ranks)")
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -448,9 +547,14 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
                      "avg_launch_us": 1e3 * d_ms / max(d_launch, 1), "launches": d_launch,
                      "algorithmic_bytes_per_launch": d_bytes / max(d_launch, 1)},
         "phases_rank0": phases,
+        "driver_phases_rank0": driver_phase_table(driver_phases, args.steps, dev_ms / args.steps),
+        "memory": {"peak_torch_allocated_GiB_max_over_ranks": round(peak_gib, 2), "device_used_GiB_max_over_ranks": round(used_gib, 2),
+                   "shard_GiB": round(8 * size / world / 2**30, 2)},
         "clocks": clocks,
         "energy_last_step": last[0],
     }
+    if parity is not None:
+        line["parity"] = parity
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = {"note": "reported by the N=1 run (rank 0, bounded sample); not repeated at N>1"}
     print(json.dumps(line), flush=True)
@@ -546,6 +650,9 @@ def main():
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: 'sharded' = one evaluation with the CI vector split by alpha rows (strong scaling); "
                          "'replicas' = independent theta sets per rank (weak scaling)")
+    ap.add_argument("--parity-golden", action="store_true",
+                    help="evaluate the committed sparse-oracle case of the workload before the timed region and report the errors")
+    ap.add_argument("--chunk-gib", type=float, default=4.0, help="N>1 sharded runs: staging budget of the row moves")
     ap.add_argument("--batch", type=int, default=0,
                     help="batched-theta mode: each step evaluates this many parameter sets in the same launches (small active spaces)")
     args = ap.parse_args()

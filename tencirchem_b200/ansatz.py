@@ -10,11 +10,16 @@ its classes with ``engine="civector-b200"`` after ``tencirchem_b200.register()``
 """
 from __future__ import annotations
 
+import logging
+import threading
 from math import comb
 from time import time
 from typing import List, Sequence, Tuple
 
 import numpy as np
+from scipy.optimize import OptimizeResult as _OptResult
+
+logger = logging.getLogger(__name__)
 
 from . import engine_ucc
 from .ci_utils import get_ci_strings
@@ -266,6 +271,14 @@ class UCC:
         """ucc.py:1033-1038."""
         return self.energy()
 
+    def _minimize_options(self) -> dict:
+        """ucc.py:355-360: the reference's strict L-BFGS-B defaults (ftol = 10 eps, gtol = 100 eps of float64)
+        unless ``scipy_minimize_options`` is set."""
+        if self.scipy_minimize_options is None:
+            eps = np.finfo(np.float64).eps
+            return {"ftol": 1e1 * eps, "gtol": 1e2 * eps}
+        return self.scipy_minimize_options
+
     def kernel(self) -> float:
         """ucc.py:337-378: L-BFGS-B over ``energy_and_grad``."""
         from scipy.optimize import minimize
@@ -275,14 +288,16 @@ class UCC:
             self.init_guess = np.zeros(self.n_params)
         if self.n_params == 0:
             e = self.energy(np.zeros(0))
-            self.opt_res = {"e": e, "x": np.zeros(0), "success": True, "init_guess": self.init_guess}
+            self.opt_res = _OptResult(e=e, fun=e, x=np.zeros(0), success=True, init_guess=self.init_guess)
             self.params = self.opt_res["x"]
             return e
         t0 = time()
         func = lambda x: tuple(np.asarray(v, dtype=np.float64) for v in self.energy_and_grad(x))
         res = minimize(func, x0=np.asarray(self.init_guess, dtype=np.float64), jac=True, method="L-BFGS-B",
-                       options=self.scipy_minimize_options)
-        opt_res = dict(res)
+                       options=self._minimize_options())
+        if not res.success:
+            logger.warning("Optimization failed. See `.opt_res` for details.")  # ucc.py:367-368
+        opt_res = _OptResult(res)
         opt_res["opt_time"] = time() - t0
         opt_res["init_guess"] = self.init_guess
         opt_res["e"] = float(res.fun)
@@ -322,6 +337,13 @@ class KUPCCGSD(UCC):
         self.k = k
         self.n_tries = n_tries
         self.ex_ops, self.param_ids, self.init_guess = self.get_ex_ops()
+        # kupccgsd.py:91-96
+        self.init_guess_list = [self.init_guess]
+        for _ in range(self.n_tries - 1):
+            self.init_guess_list.append(np.random.rand(self.n_params) - 0.5)
+        self.e_tries_list = []
+        self.opt_res_list = []
+        self.staging_time = self.opt_time = None
 
     def get_ex1_ops(self):
         n = self.no + self.nv
@@ -348,17 +370,100 @@ class KUPCCGSD(UCC):
         return ops, ids, np.random.rand(max(ids) + 1 if ids else 0) - 0.5
 
     def kernel(self):
-        """kupccgsd.py:98-125: best of ``n_tries`` random starts."""
-        best = None
-        for _ in range(self.n_tries):
-            self.init_guess = np.random.rand(self.n_params) - 0.5
+        """kupccgsd.py:98-125: best of ``n_tries`` starts (``init_guess_list``).  With n_tries > 1 the L-BFGS-B runs
+        advance in LOCK STEP: every iteration evaluates the current point of all unfinished tries in one batched call
+        (``energy_and_grad_batch`` -> tcc_energy_and_grad_batch: all parameter sets share every kernel launch) instead
+        of the reference's serial loop of restarts."""
+        self._sanity_check()
+        t0 = time()
+        if self.n_tries == 1:
+            if not np.allclose(self.init_guess, self.init_guess_list[0]):
+                logger.info("Inconsistent `self.init_guess` and `self.init_guess_list`.  Use `self.init_guess`.")
             super().kernel()
-            if best is None or self.opt_res["e"] < best["e"]:
-                best = self.opt_res
-        self.opt_res = best
-        self.params = best["x"].copy()
-        self.init_guess = best["init_guess"]
-        return float(best["e"])
+            results = [self.opt_res]
+        else:
+            results = lockstep_minimize(self.energy_and_grad_batch, self.init_guess_list[: self.n_tries], self._minimize_options())
+        self.opt_res_list = sorted(results, key=lambda r: r.fun)
+        self.e_tries_list = [float(r.fun) for r in self.opt_res_list]
+        self.opt_time = time() - t0
+        self.opt_res = self.opt_res_list[0]
+        self.opt_res["e"] = float(self.opt_res.fun)
+        self.opt_res["e_tries"] = self.e_tries_list
+        if not self.opt_res.success:
+            logger.warning("Optimization failed. See `.opt_res` for details.")
+        self.params = np.array(self.opt_res.x, dtype=np.float64)
+        self.init_guess = self.opt_res.init_guess
+        return float(self.opt_res.e)
+
+
+def lockstep_minimize(fun_batch, x0_list, options=None, method="L-BFGS-B"):
+    """Runs one SciPy L-BFGS-B per starting point, all in lock step: each optimiser lives in its own thread and blocks
+    in its objective call until every unfinished optimiser has asked for a point; the points are then evaluated by ONE
+    call ``fun_batch(thetas[B, P]) -> (energies[B], grads[B, P])``.  Every try follows exactly the iterates of a serial
+    run (same algorithm, same options); only the evaluation is shared.  Returns the list of OptimizeResult (with
+    ``init_guess`` and ``e``), in the order of ``x0_list``."""
+    from scipy.optimize import minimize
+
+    n = len(x0_list)
+    cond = threading.Condition()
+    pending, answers, errors = {}, {}, []
+    state = {"active": n, "batches": 0, "evals": 0}
+
+    def flush_locked():
+        ids = sorted(pending)
+        try:
+            e, g = fun_batch(np.stack([pending[i] for i in ids]))
+            for k, i in enumerate(ids):
+                answers[i] = (float(e[k]), np.array(g[k], dtype=np.float64))
+        except BaseException as exc:  # hand the failure to every waiting optimiser
+            errors.append(exc)
+            for i in ids:
+                answers[i] = None
+        state["batches"] += 1
+        state["evals"] += len(ids)
+        pending.clear()
+        cond.notify_all()
+
+    def objective(i, x):
+        with cond:
+            pending[i] = np.array(x, dtype=np.float64)
+            if len(pending) == state["active"]:
+                flush_locked()
+            else:
+                cond.wait_for(lambda: i in answers)
+            ans = answers.pop(i)
+        if ans is None:
+            raise RuntimeError("batched evaluation failed") from errors[0]
+        return ans
+
+    results = [None] * n
+
+    def run(i):
+        try:
+            res = minimize(lambda x: objective(i, x), x0=np.asarray(x0_list[i], dtype=np.float64), jac=True, method=method,
+                           options=options)
+            res["init_guess"] = x0_list[i]
+            res["e"] = float(res.fun)
+            results[i] = res
+        except BaseException as exc:
+            errors.append(exc)
+        finally:
+            with cond:
+                state["active"] -= 1
+                if pending and len(pending) == state["active"]:
+                    flush_locked()
+
+    threads = [threading.Thread(target=run, args=(i,), daemon=True) for i in range(n)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errors:
+        raise errors[0]
+    for r in results:
+        r["lockstep_batches"] = state["batches"]
+        r["lockstep_evals"] = state["evals"]
+    return results
 
 
 class PUCCD(UCC):

@@ -458,10 +458,11 @@ void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& 
 }
 
 // out[a, b] = in[map_a[a], map_b[b]]  (storage order <-> reference order)
-__global__ void __launch_bounds__(256) permute_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t na, int64_t nb,
+__global__ void __launch_bounds__(256) permute_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t row0, int64_t nb,
                                                       const uint32_t* __restrict__ map_a, const uint32_t* __restrict__ map_b) {
+    // `out` and `map_a` are already offset to row0 (row chunk of the launch); an identity row map reads row0 + a
     const int64_t a = blockIdx.y;
-    const int64_t src_row = (map_a ? int64_t(map_a[a]) : a) * nb;
+    const int64_t src_row = (map_a ? int64_t(map_a[a]) : row0 + a) * nb;
     for (int64_t b = int64_t(blockIdx.x) * 256 + threadIdx.x; b < nb; b += int64_t(gridDim.x) * 256)
         out[a * nb + b] = in[src_row + map_b[b]];
 }
@@ -471,7 +472,7 @@ void launch_permute(const double* in, double* out, int64_t na, int64_t nb, const
     unsigned gx = unsigned(std::min<int64_t>((nb + 255) / 256, 64));
     for (int64_t r0 = 0; r0 < na; r0 += 65535) {
         unsigned gy = unsigned(std::min<int64_t>(na - r0, 65535));
-        permute_kernel<<<dim3(gx, gy, 1), 256, 0, st>>>(in, out + r0 * nb, gy, nb, map_a ? map_a + r0 : nullptr, map_b);
+        permute_kernel<<<dim3(gx, gy, 1), 256, 0, st>>>(in, out + r0 * nb, r0, nb, map_a ? map_a + r0 : nullptr, map_b);
     }
 }
 

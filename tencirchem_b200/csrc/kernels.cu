@@ -198,6 +198,10 @@ reverse_kernel(double* __restrict__ ket, double* __restrict__ bra, int64_t nb, c
 
 void launch_reverse(double* ket, double* bra, int64_t nb, SideList rows, SideList cols, double cs, double sn_s0,
                     double s0, double* partials, unsigned* ticket, double* grad_out, cudaStream_t st) {
+    if (rows.len <= 0 || cols.len <= 0) {  // empty support: nothing to rotate, the gradient term is zero
+        cudaMemsetAsync(grad_out, 0, sizeof(double), st);
+        return;
+    }
     dim3 grid = pair_grid(rows.len, cols.len);
     bool rid = rows.src == nullptr, cid = cols.src == nullptr;
     if (rid && !cid)

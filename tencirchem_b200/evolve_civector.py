@@ -13,12 +13,20 @@ import numpy as np
 
 from .plan import Plan
 
-_PLAN_CACHE: dict = {}
+from collections import OrderedDict
+
+_PLAN_CACHE: "OrderedDict" = OrderedDict()  # least recently used first
 _MAX_CACHED = 8
+# device-memory bound of the cache: tables plus the lazily allocated workspaces (up to six full vectors per plan)
+_MAX_CACHED_BYTES = 48 << 30
 
 
 def clear_cache():
     _PLAN_CACHE.clear()
+
+
+def _plan_footprint(plan: Plan) -> int:
+    return int(plan.device_bytes)
 
 
 def default_device() -> int:
@@ -44,11 +52,15 @@ def get_plan(n_qubits, n_elec, ex_ops, param_ids, hcb=False, device=None) -> Pla
         param_ids = range(len(ex_ops))
     key = (n_qubits, n_elec, ex_ops, tuple(param_ids), bool(hcb), device)
     plan = _PLAN_CACHE.get(key)
-    if plan is None:
-        if len(_PLAN_CACHE) >= _MAX_CACHED:
-            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-        plan = Plan(n_qubits, n_elec, ex_ops, param_ids, hcb=hcb, device=device)
-        _PLAN_CACHE[key] = plan
+    if plan is not None:
+        _PLAN_CACHE.move_to_end(key)  # LRU: a hit makes the plan the most recently used
+        return plan
+    # evict least recently used plans while the cache is over its count or device-memory bound (ADAPT-style loops
+    # create a new key per iteration; every plan pins its tables and workspaces until it is dropped)
+    while _PLAN_CACHE and (len(_PLAN_CACHE) >= _MAX_CACHED or sum(_plan_footprint(q) for q in _PLAN_CACHE.values()) > _MAX_CACHED_BYTES):
+        _PLAN_CACHE.popitem(last=False)
+    plan = Plan(n_qubits, n_elec, ex_ops, param_ids, hcb=hcb, device=device)
+    _PLAN_CACHE[key] = plan
     return plan
 
 

@@ -2,7 +2,8 @@
 multi-start kUpCCGSD, ADAPT pools) shard across ranks with no data-path collective; only (E, grad E) are gathered.
 One process per GPU, `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) for the plumbing.
 
-The alpha-sharded single-vector regime ((20e,20o)) is designed in DESIGN.md section 6 and not built yet.
+The other regime -- ONE CI vector sharded by alpha rows over the GPUs, (18e,18o) / (20e,20o) -- lives in
+tencirchem_b200/sharded.py.
 """
 from __future__ import annotations
 

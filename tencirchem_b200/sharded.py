@@ -3,9 +3,10 @@
 Every rank holds the rows of the [na, nb] CI matrix whose occupation pattern on t = log2(world) alpha orbitals T
 equals its rank.  T is chosen per batch among the orbitals that are not active on the alpha side of the batch
 (include/tcc_b200.h, multi-GPU section), so all batch kernels run on local rows; only when T changes do rows move
-between ranks (one all-to-all per vector).  H c works on row blocks of the gathered vector (`tcc_apply_h_rows`) and
-is summed with an all-reduce, which needs the full vector on every GPU: fine up to (18e,18o) (18.9 GB); the
-(20e,20o) vector needs the three-layout sigma of DESIGN.md section 6 instead (not built).
+between ranks (one all-to-all per vector).  H c has two modes: "replicated" works on row blocks of the gathered
+vector (`tcc_apply_h_rows`), which needs the full vector on every GPU (fine up to (18e,18o), 18.9 GB);
+"distributed" keeps the vector sharded (three alpha-beta passes in layouts with disjoint T plus a column transpose
+for the alpha-alpha terms, `tcc_shard_sigma_*`), which is what the 273 GB (20e,20o) vector needs.
 
 The same driver runs
 * one rank per process over `torch.distributed` (NCCL; `TorchComm`), and
@@ -22,6 +23,66 @@ import numpy as np
 
 from .plan import Plan
 from .parallel import shard_bounds
+
+
+class PhaseTimer:
+    """Per-phase device time (CUDA events on the current stream) and host time of the sharded driver.  Off by default;
+    `bench.py` turns it on for `phases_rank0`.  The device time of a collective is the span the compute stream waited
+    for it (torch's NCCL calls make the current stream wait for the communication stream)."""
+
+    def __init__(self, torch_mod, enabled=False):
+        self.t = torch_mod
+        self.enabled = enabled
+        self.reset()
+
+    def reset(self):
+        self._spans = []  # (name, ev0, ev1)
+        self.host_s = {}
+        self.bytes = {}
+
+    class _Span:
+        def __init__(self, owner, name, nbytes):
+            self.o, self.name, self.nbytes = owner, name, nbytes
+
+        def __enter__(self):
+            o = self.o
+            if o.enabled:
+                import time
+
+                self.ev0 = o.t.cuda.Event(enable_timing=True)
+                self.ev0.record()
+                self.t0 = time.perf_counter()
+            return self
+
+        def __exit__(self, *exc):
+            o = self.o
+            if o.enabled:
+                import time
+
+                ev1 = o.t.cuda.Event(enable_timing=True)
+                ev1.record()
+                o._spans.append((self.name, self.ev0, ev1))
+                o.host_s[self.name] = o.host_s.get(self.name, 0.0) + time.perf_counter() - self.t0
+                o.bytes[self.name] = o.bytes.get(self.name, 0) + int(self.nbytes)
+            return False
+
+    def phase(self, name, nbytes=0):
+        return PhaseTimer._Span(self, name, nbytes)
+
+    def summary(self):
+        """{phase: {"device_ms", "host_ms", "calls", "bytes"}} accumulated since reset()"""
+        if not self.enabled:
+            return {}
+        self.t.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self._spans:
+            d = out.setdefault(name, {"device_ms": 0.0, "host_ms": 0.0, "calls": 0, "bytes": 0})
+            d["device_ms"] += e0.elapsed_time(e1)
+            d["calls"] += 1
+        for name, d in out.items():
+            d["host_ms"] = 1e3 * self.host_s.get(name, 0.0)
+            d["bytes"] = self.bytes.get(name, 0)
+        return out
 
 
 class LocalComm:
@@ -47,6 +108,27 @@ class LocalComm:
             total += t
         for t in tensors:
             t.copy_(total)
+
+    def all_gather_padded(self, blocks, max_rows):
+        """blocks[i]: [rows_i, nb] of local rank i -> per local rank a [world, max_rows, nb] tensor whose slab s holds
+        the rows of rank s (rows beyond rows_s are undefined)"""
+        import torch
+
+        out = torch.empty((self.world, max_rows) + tuple(blocks[0].shape[1:]), dtype=blocks[0].dtype, device=blocks[0].device)
+        for s_, b in enumerate(blocks):
+            out[s_, : b.shape[0]] = b
+        return [out for _ in blocks]
+
+    def reduce_scatter_sum(self, stacked):
+        """stacked[i]: [world, max_rows, nb] of local rank i (slab d = its contribution to rank d) -> per local rank the
+        [max_rows, nb] sum over all ranks of their slab for it"""
+        outs = []
+        for d in range(self.world):
+            acc = stacked[0][d].clone()
+            for s_ in range(1, self.world):
+                acc += stacked[s_][d]
+            outs.append(acc)
+        return outs
 
 
 class TorchComm:
@@ -99,6 +181,27 @@ class TorchComm:
         (t,) = tensors
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
 
+    def all_gather_padded(self, blocks, max_rows):
+        import torch
+
+        (b,) = blocks
+        inp = torch.empty((max_rows,) + tuple(b.shape[1:]), dtype=b.dtype, device=b.device)
+        inp[: b.shape[0]] = b
+        out = torch.empty((self.world, max_rows) + tuple(b.shape[1:]), dtype=b.dtype, device=b.device)
+        self.dist.all_gather_into_tensor(out.view(self.world * max_rows, -1), inp.view(max_rows, -1))
+        return [out]
+
+    def reduce_scatter_sum(self, stacked):
+        import torch
+
+        (x,) = stacked
+        if self.dist.get_backend() == "nccl":
+            out = torch.empty(tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+            self.dist.reduce_scatter_tensor(out, x, op=self.dist.ReduceOp.SUM)
+            return [out]
+        self.dist.all_reduce(x, op=self.dist.ReduceOp.SUM)  # gloo (CPU tests) has no reduce-scatter
+        return [x[self.rank].clone()]
+
 
 class RowMover:
     """Moves the rows of local [rows, nb] matrices between the row layouts of a sharded plan.  Host logic only
@@ -120,6 +223,7 @@ class RowMover:
         self._moves = {}
         self._rows_dev = {}
         self.reshards = 0
+        self.timer = PhaseTimer(torch, False)
 
     def rows_dev(self, layout: int, rank: int):
         """Storage rows of `rank` in `layout` as an index tensor on the device (cached)."""
@@ -167,11 +271,16 @@ class RowMover:
         for j in range(len(plans[0][0])):
             rnd = [mp[0][j] for mp in plans]
             # pack the rows by destination (one gather), one all-to-all, unpack by local row (one scatter)
-            send = [v.index_select(0, r_[0]) for v, r_ in zip(vecs, rnd)]
-            recv = self.comm.exchange_packed(send, [r_[2] for r_ in rnd], [r_[3] for r_ in rnd])
-            for new, r_, got in zip(out, rnd, recv):
-                if r_[1].numel():
-                    new.index_copy_(0, r_[1], got)
+            with self.timer.phase("move_pack"):
+                send = [v.index_select(0, r_[0]) for v, r_ in zip(vecs, rnd)]
+            with self.timer.phase("move_all_to_all", sum(int(x.numel()) * 8 for x in send)):
+                recv = self.comm.exchange_packed(send, [r_[2] for r_ in rnd], [r_[3] for r_ in rnd])
+            del send
+            with self.timer.phase("move_unpack"):
+                for new, r_, got in zip(out, rnd, recv):
+                    if r_[1].numel():
+                        new.index_copy_(0, r_[1], got)
+            del recv
         return out
 
     # ---- row-sharded [rows, nb]  <->  column-sharded [na, cols] (all rows, a block of columns) ----------------
@@ -273,7 +382,9 @@ class ShardedUCC:
         self.segments = p0.shard_segments()
         self.mover = RowMover(p0, comm, self.device, chunk_bytes)
         self.rows = self.mover.rows
-        self.hf_row = int(p0.storage_order()[0])  # HF determinant = reference address 0 of both spins
+        self.timer = self.mover.timer  # one PhaseTimer for the driver and its row mover (off unless enabled)
+        self.ref2int = p0.storage_order()  # storage address of every per-spin string, by reference address
+        self.hf_row = int(self.ref2int[0])  # HF determinant = reference address 0 of both spins
 
     @property
     def reshards(self) -> int:
@@ -287,37 +398,58 @@ class ShardedUCC:
         return self.mover.reshard(vecs, l_from, l_to)
 
     # ---- the path -----------------------------------------------------------------------------------
-    def _forward(self, params):
+    def _forward(self, params, init_sparse=None):
+        """init_sparse = (alpha reference addresses, beta reference addresses, amplitudes) of the non-zeros of an
+        initial state (the dense `init_state` of get_civector, evolve_civector.py:189-193, does not exist at the sizes
+        this engine is for); None = the HF determinant."""
         t = self.torch
         first = self.segments[0][0] if self.segments else 0
+        if init_sparse is None:
+            ia, ib, iv = np.array([self.hf_row]), np.array([self.hf_row]), np.array([1.0])
+        else:
+            ia = self.ref2int[np.asarray(init_sparse[0], dtype=np.int64)].astype(np.int64)
+            ib = self.ref2int[np.asarray(init_sparse[1], dtype=np.int64)].astype(np.int64)
+            iv = np.asarray(init_sparse[2], dtype=np.float64)
         kets = []
         for st in self.states:
             st.plan.shard_set_params(params)
             rows = self.rows[first][st.rank]
             ket = t.zeros((len(rows), self.nb), dtype=t.float64, device=self.device)
-            pos = np.searchsorted(rows, self.hf_row)
-            if pos < len(rows) and rows[pos] == self.hf_row:
-                ket[pos, self.hf_row] = 1.0
+            pos = np.searchsorted(rows, ia)
+            pos[pos >= len(rows)] = 0
+            mine = (rows[pos] == ia) if len(rows) else np.zeros(len(ia), dtype=bool)
+            if mine.any():
+                flat = t.as_tensor(pos[mine] * self.nb + ib[mine], dtype=t.int64, device=self.device)
+                ket.view(-1).index_put_((flat,), t.as_tensor(iv[mine], dtype=t.float64, device=self.device))
             kets.append(ket)
             del ket
         layout = first
         for seg, (l, _, _) in enumerate(self.segments):
             kets = self._reshard(kets, layout, l)
             layout = l
-            for k, st in enumerate(self.states):
-                if kets[k].numel():  # a rank may own no row in a layout of a tiny active space
-                    st.plan.shard_forward(seg, kets[k])
+            with self.timer.phase("forward_kernels"):
+                for k, st in enumerate(self.states):
+                    if kets[k].numel():  # a rank may own no row in a layout of a tiny active space
+                        st.plan.shard_forward(seg, kets[k])
         return kets, layout
 
     def _gather_full(self, vecs, layout):
-        """Full [na, nb] storage-order matrix on every rank (zero-padded own rows, summed)."""
+        """Full [na, nb] storage-order matrix on every rank: one all-gather of the (padded) row blocks, then the rows
+        of every source rank are copied to their storage positions."""
         t = self.torch
+        max_rows = max(len(r) for r in self.rows[layout])
+        with self.timer.phase("sigma_all_gather", 8 * max_rows * self.nb * (self.world - 1)):
+            gathered = self.comm.all_gather_padded(vecs, max_rows)
         fulls = []
-        for st, v in zip(self.states, vecs):
-            full = t.zeros((self.na, self.nb), dtype=t.float64, device=self.device)
-            full.index_copy_(0, self.mover.rows_dev(layout, st.rank), v)
-            fulls.append(full)
-        self.comm.all_reduce_sum(fulls)
+        with self.timer.phase("sigma_unpack"):
+            for g in gathered:
+                full = t.empty((self.na, self.nb), dtype=t.float64, device=self.device)
+                for s_ in range(self.world):
+                    n_s = len(self.rows[layout][s_])
+                    if n_s:
+                        full.index_copy_(0, self.mover.rows_dev(layout, s_), g[s_, :n_s])
+                fulls.append(full)
+                del full
         return fulls
 
     def _sigma_distributed(self, kets, layout):
@@ -327,10 +459,12 @@ class ShardedUCC:
         l3 = self.states[0].plan.shard_sigma_layouts()
         sig = []
         for st, ket in zip(self.states, kets):
-            s_loc = t.zeros_like(ket)
-            if ket.numel():
-                st.plan.shard_sigma_bb(ket, s_loc)
+            with self.timer.phase("sigma_kernels"):
+                s_loc = t.zeros_like(ket)
+                if ket.numel():
+                    st.plan.shard_sigma_bb(ket, s_loc)
             sig.append(s_loc)
+            del s_loc
         # alpha-beta: pass i in layout l3[i].  The passes live in helper methods: a tensor that a loop variable of this
         # frame still names would stay allocated through the next pass (a fifth shard at (20e,20o) is an OOM).
         for i, l in enumerate(l3):
@@ -342,20 +476,33 @@ class ShardedUCC:
         return sig
 
     def _sigma_replicated(self, kets, layout):
-        """sigma = H c on the all-reduced full vector: every rank contracts a block of rows, the blocks are summed and
-        each rank keeps its rows.  Two full vectors per GPU."""
+        """sigma = H c on the gathered full vector: every rank contracts a block of source rows, the partial results are
+        packed by destination rank and summed with ONE reduce-scatter (each rank receives only its rows).  Two to three
+        full vectors per GPU."""
         t = self.torch
         c_full = self._gather_full(kets, layout)
-        s_full = []
+        max_rows = max(len(r) for r in self.rows[layout])
+        stacked = []
         for k, st in enumerate(self.states):
-            sig = t.zeros_like(c_full[k])
-            lo, hi = shard_bounds(self.na, st.rank, self.world)
-            st.plan.apply_h_rows(c_full[k], sig, lo, hi - lo)
-            s_full.append(sig)
-            del sig
+            with self.timer.phase("sigma_kernels"):
+                sig = t.zeros_like(c_full[k])
+                lo, hi = shard_bounds(self.na, st.rank, self.world)
+                st.plan.apply_h_rows(c_full[k], sig, lo, hi - lo)
+            with self.timer.phase("sigma_pack"):
+                buf = t.empty((self.world, max_rows, self.nb), dtype=t.float64, device=self.device)
+                for d in range(self.world):
+                    n_d = len(self.rows[layout][d])
+                    if n_d:
+                        t.index_select(sig, 0, self.mover.rows_dev(layout, d), out=buf[d, :n_d])
+                    if n_d < max_rows:
+                        buf[d, n_d:].zero_()
+            stacked.append(buf)
+            del sig, buf
         del c_full
-        self.comm.all_reduce_sum(s_full)
-        return [s_full[k].index_select(0, self.mover.rows_dev(layout, st.rank)) for k, st in enumerate(self.states)]
+        with self.timer.phase("sigma_reduce_scatter", 8 * max_rows * self.nb * (self.world - 1)):
+            mine = self.comm.reduce_scatter_sum(stacked)
+        del stacked
+        return [mine[k][: len(self.rows[layout][st.rank])] for k, st in enumerate(self.states)]
 
     def _sigma_ab_pass(self, i, l, kets, layout, sig):
         """sig += pass i of the opposite-spin terms.  Peak: kets + sig + the moved copy + its partial sigma."""
@@ -363,50 +510,56 @@ class ShardedUCC:
         c_i = self._reshard(kets, layout, l)
         part = []
         for k in range(len(self.states)):
-            s_i = t.zeros_like(c_i[k])
-            if s_i.numel():
-                self.states[k].plan.shard_sigma_ab(i, c_i[k], s_i)
+            with self.timer.phase("sigma_kernels"):
+                s_i = t.zeros_like(c_i[k])
+                if s_i.numel():
+                    self.states[k].plan.shard_sigma_ab(i, c_i[k], s_i)
             part.append(s_i)
             del s_i
         del c_i
         part = self._reshard(part, l, layout)
-        for k in range(len(sig)):
-            sig[k] += part[k]
+        with self.timer.phase("sigma_accumulate"):
+            for k in range(len(sig)):
+                sig[k] += part[k]
 
     def _sigma_aa_piece(self, j, pieces, kets, layout, sig):
         t = self.torch
-        cols = self.mover.to_columns(kets, layout, j, pieces)
+        with self.timer.phase("sigma_aa_to_columns"):
+            cols = self.mover.to_columns(kets, layout, j, pieces)
         s_cols = []
         for k in range(len(self.states)):
-            out = t.empty_like(cols[k])
-            if out.numel():
-                self.states[k].plan.shard_sigma_aa(cols[k], out)
+            with self.timer.phase("sigma_kernels"):
+                out = t.empty_like(cols[k])
+                if out.numel():
+                    self.states[k].plan.shard_sigma_aa(cols[k], out)
             s_cols.append(out)
             del out
         del cols
-        self.mover.to_rows(s_cols, layout, j, pieces, add_into=sig)
+        with self.timer.phase("sigma_aa_to_rows"):
+            self.mover.to_rows(s_cols, layout, j, pieces, add_into=sig)
 
-    def civector(self, params) -> np.ndarray:
+    def civector(self, params, init_sparse=None) -> np.ndarray:
         """Reference-order CI vector on the host (small systems / tests: gathers the full vector)."""
         t = self.torch
-        kets, layout = self._forward(np.asarray(params, dtype=np.float64))
+        kets, layout = self._forward(np.asarray(params, dtype=np.float64), init_sparse)
         full = self._gather_full(kets, layout)[0].reshape(-1)
         out = t.empty_like(full)
         self.states[0].plan.from_storage_order_dev(full, out)
         t.cuda.synchronize()
         return out.cpu().numpy()
 
-    def energy_and_grad(self, params, want_grad: bool = True):
+    def energy_and_grad(self, params, want_grad: bool = True, init_sparse=None):
         t = self.torch
         params = np.asarray(params, dtype=np.float64)
-        kets, layout = self._forward(params)
+        kets, layout = self._forward(params, init_sparse)
         if self.sigma_mode == "distributed":
             bras = self._sigma_distributed(kets, layout)
         else:
             bras = self._sigma_replicated(kets, layout)
-        parts = [t.dot(bra.reshape(-1), ket.reshape(-1)).reshape(1) for bra, ket in zip(bras, kets)]  # no temporary
-        self.comm.all_reduce_sum(parts)
-        energy = float(parts[0][0])
+        with self.timer.phase("energy_dot_allreduce"):
+            parts = [t.dot(bra.reshape(-1), ket.reshape(-1)).reshape(1) for bra, ket in zip(bras, kets)]  # no temporary
+            self.comm.all_reduce_sum(parts)
+            energy = float(parts[0][0])
         if not want_grad:
             return energy, None
         fuse = self.fuse_reverse_moves
@@ -414,27 +567,32 @@ class ShardedUCC:
             total = t.cuda.get_device_properties(self.device).total_memory
             fuse = self.world > 1 and 2 * 8 * max(k_.numel() for k_ in kets) < total // 8
         if fuse:
-            both = [t.stack((kets[k], bras[k]), dim=1) for k in range(len(kets))]  # [rows, 2, nb]
+            with self.timer.phase("reverse_interleave"):
+                both = [t.stack((kets[k], bras[k]), dim=1) for k in range(len(kets))]  # [rows, 2, nb]
             del kets, bras
             for seg in range(len(self.segments) - 1, -1, -1):
                 l = self.segments[seg][0]
                 both = self._reshard(both, layout, l)
                 layout = l
-                for k, st in enumerate(self.states):
-                    if both[k].numel():
-                        st.plan.shard_reverse_strided(seg, both[k][:, 0], both[k][:, 1], 2 * self.nb)
+                with self.timer.phase("reverse_kernels"):
+                    for k, st in enumerate(self.states):
+                        if both[k].numel():
+                            st.plan.shard_reverse_strided(seg, both[k][:, 0], both[k][:, 1], 2 * self.nb)
         else:
             for seg in range(len(self.segments) - 1, -1, -1):
                 l = self.segments[seg][0]
                 kets = self._reshard(kets, layout, l)
                 bras = self._reshard(bras, layout, l)
                 layout = l
-                for k, st in enumerate(self.states):  # by index: no loop variable keeps a shard of the old layout alive
-                    if kets[k].numel():
-                        st.plan.shard_reverse(seg, kets[k], bras[k])
-        grads = [t.as_tensor(st.plan.shard_gradient(), dtype=t.float64, device=self.device) for st in self.states]
-        self.comm.all_reduce_sum(grads)
-        return energy, grads[0].cpu().numpy()
+                with self.timer.phase("reverse_kernels"):
+                    for k, st in enumerate(self.states):  # by index: no loop variable keeps a shard of the old layout alive
+                        if kets[k].numel():
+                            st.plan.shard_reverse(seg, kets[k], bras[k])
+        with self.timer.phase("gradient_allreduce"):
+            grads = [t.as_tensor(st.plan.shard_gradient(), dtype=t.float64, device=self.device) for st in self.states]
+            self.comm.all_reduce_sum(grads)
+            out = grads[0].cpu().numpy()
+        return energy, out
 
     def energy(self, params) -> float:
         return self.energy_and_grad(params, want_grad=False)[0]

@@ -99,6 +99,20 @@ def _reshard_worker(rank, world, port, out):
     ok = ok and torch.equal(cols[0], full[:, lo:hi])
     back = mover.to_rows(cols, layout)
     ok = ok and torch.equal(back[0], local[0])
+    # the collectives of the replicated H c: all-gather of padded row blocks, reduce-scatter of packed partial sums
+    comm = mover.comm
+    max_rows = max(len(r) for r in mover.rows[layout])
+    gathered = comm.all_gather_padded(local, max_rows)[0]
+    for s_ in range(world):
+        n_s = len(mover.rows[layout][s_])
+        ok = ok and torch.equal(gathered[s_, :n_s], full[torch.as_tensor(mover.rows[layout][s_])])
+    stacked = torch.zeros((world, max_rows, na), dtype=torch.float64)
+    for d in range(world):
+        n_d = len(mover.rows[layout][d])
+        stacked[d, :n_d] = (rank + 1) * full[torch.as_tensor(mover.rows[layout][d])]
+    mine = comm.reduce_scatter_sum([stacked])[0]
+    n_me = len(mover.rows[layout][rank])
+    ok = ok and torch.equal(mine[:n_me], sum(range(1, world + 1)) * full[torch.as_tensor(mover.rows[layout][rank])])
     # ownership is a partition of the rows in every layout
     for own in mover.owner:
         ok = ok and own.min() >= 0 and own.max() < world and len(own) == na

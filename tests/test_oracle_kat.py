@@ -287,3 +287,58 @@ def test_rdm_oracle_reproduces_the_reference_docstring_example_h2():
     rdm1, rdm2 = R.make_rdm12(c, 2, 2)
     e = int1e.ravel() @ rdm1.ravel() + 0.5 * int2e.ravel() @ rdm2.ravel()
     assert abs(e + k["e_nuc"] - k["e_ucc"]) < 1e-8  # the published amplitudes carry 9 digits
+
+
+# ---- sparse oracle (oracle/sparse.py): pinned against the dense restatement ---------------------------------------
+@pytest.mark.parametrize("n", [2, 3, 4, 6])
+def test_sparse_oracle_matches_dense_oracle(n):
+    """Energy, all gradients, state, sigma on the full space and G|c> of the sparse (dict-of-determinants) oracle equal
+    the dense oracle's for full UCCSD with dense random parameters."""
+    from oracle import sparse as S
+
+    no = n // 2
+    ex_ops, pids = pools.uccsd_ex_ops(no, n - no)
+    int1e, int2e = O.random_integral(n)
+    np.random.seed(2077)
+    params = np.random.rand(max(pids) + 1) - 0.5
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, n)
+    e_ref, g_ref = O.get_energy_and_grad(params, h, 2 * n, n, ex_ops, pids)
+    c_ref = O.get_civector(params, 2 * n, n, ex_ops, pids)
+    e, g, psi, _ = S.get_energy_and_grad(params, int1e, int2e, 2 * n, n, ex_ops, pids)
+    assert abs(e - e_ref) < 1e-13
+    assert np.abs(np.array([g[p] for p in range(len(params))]) - g_ref).max() < 1e-13
+    assert np.abs(S.to_dense(psi, 2 * n, n) - c_ref).max() < 1e-14
+    ci = O.get_ci_strings(2 * n, n, False)
+    assert np.abs(S.apply_h(psi, int1e, int2e, n, ci) - h(c_ref)).max() < 1e-13
+    for f in list(ex_ops[:4]) + list(ex_ops[-4:]):
+        a = S.to_dense(S.apply_excitation(psi, 2 * n, f), 2 * n, n)
+        assert np.abs(a - O.apply_excitation(c_ref, 2 * n, n, f, False)).max() < 1e-14
+    O.clear_cache()
+
+
+def test_sparse_golden_8o_matches_dense_oracle():
+    """The committed sparse known answers are what the dense oracle gives: the (8e,8o) case of make_sparse_golden.py
+    (sparse random initial state, a few non-zero parameters of every kind, full UCCSD op list) re-evaluated densely."""
+    import json
+    import os
+
+    from oracle import sparse as S
+
+    case = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sparse_parity_8o.json")))
+    n = case["n_orb"]
+    ex_ops, pids = pools.uccsd_ex_ops(n // 2, n - n // 2)
+    int1e, int2e = O.random_integral(n)
+    params = np.zeros(case["n_params"])
+    params[case["param_ids_nonzero"]] = case["param_values"]
+    ci = O.get_ci_strings(2 * n, n, False)
+    init = S._lookup(np.array(case["init_strings"], dtype=np.uint64), np.array(case["init_amps"]), ci)
+    h = O.get_h_fcifunc_from_integral(int1e, int2e, n)
+    e, g = O.get_energy_and_grad(params, h, 2 * n, n, ex_ops, pids, init_state=init)
+    assert abs(e - case["energy"]) < 1e-13
+    assert np.abs(g[case["grad_ids"]] - case["grad_values"]).max() < 1e-13
+    c = O.get_civector(params, 2 * n, n, ex_ops, pids, init_state=init)
+    pos = np.searchsorted(ci, np.array(case["psi_sample_strings"], dtype=np.uint64))
+    assert np.abs(c[pos] - case["psi_sample_amps"]).max() < 1e-14
+    pos = np.searchsorted(ci, np.array(case["sigma_sample_strings"], dtype=np.uint64))
+    assert np.abs(h(c)[pos] - case["sigma_sample_values"]).max() < 1e-13
+    O.clear_cache()

@@ -538,6 +538,17 @@ class ShardedUCC:
         with self.timer.phase("sigma_aa_to_rows"):
             self.mover.to_rows(s_cols, layout, j, pieces, add_into=sig)
 
+    def _dot(self, x, y):
+        """<x|y> of two local blocks as a 1-element device tensor, without a temporary; in slices of at most 2^30
+        elements (the BLAS dot behind torch.dot takes 32-bit lengths; a (20e,20o) shard has 4.5e9 elements)."""
+        t = self.torch
+        xf, yf = x.reshape(-1), y.reshape(-1)
+        acc = t.zeros(1, dtype=t.float64, device=self.device)
+        step = 1 << 30
+        for lo in range(0, xf.numel(), step):
+            acc += t.dot(xf[lo:lo + step], yf[lo:lo + step])
+        return acc
+
     def civector(self, params, init_sparse=None) -> np.ndarray:
         """Reference-order CI vector on the host (small systems / tests: gathers the full vector)."""
         t = self.torch
@@ -557,7 +568,7 @@ class ShardedUCC:
         else:
             bras = self._sigma_replicated(kets, layout)
         with self.timer.phase("energy_dot_allreduce"):
-            parts = [t.dot(bra.reshape(-1), ket.reshape(-1)).reshape(1) for bra, ket in zip(bras, kets)]  # no temporary
+            parts = [self._dot(bra, ket) for bra, ket in zip(bras, kets)]
             self.comm.all_reduce_sum(parts)
             energy = float(parts[0][0])
         if not want_grad:

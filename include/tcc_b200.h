@@ -174,6 +174,19 @@ int tcc_shard_reverse(tcc_plan* plan, int seg, double* ket_local_dev, double* br
  * [rows, 2, nb] block, so that a single row move between segments serves both vectors */
 int tcc_shard_reverse_strided(tcc_plan* plan, int seg, double* ket_local_dev, double* bra_local_dev,
                               int64_t row_stride, void* stream);
+/* the same on ONE block of interleaved elements kb_local = [local rows][num_strings][2], (ket, bra) of a determinant
+ * side by side: a single row move between segments serves both vectors and the kernel gathers / rotates 16-byte
+ * elements.  tcc_shard_can_interleave() is 1 when every batch of the plan supports it. */
+int tcc_shard_reverse_interleaved(tcc_plan* plan, int seg, double* kb_local_dev, void* stream);
+int tcc_shard_can_interleave(const tcc_plan* plan);
+/* Row move between two row layouts over PEER MEMORY (NVLink / NVSwitch): the i-th moved local row src[src_row[i], :]
+ * is written straight into row dst_row[i] of the destination block of rank dst_rank[i], whose base address as mapped
+ * into this process is peer_base[dst_rank[i]] (a symmetric allocation; the own rank's entry is a local address).  One
+ * pass of 16-byte stores: no pack buffer, no collective, no unpack.  The caller orders it against the peers' use of the
+ * destination block (a stream barrier after the push).  All pointers are device pointers of `device`. */
+int tcc_push_rows(int device, const double* src_dev, int64_t row_doubles, int64_t n_rows, const int64_t* src_row_dev,
+                  const int64_t* dst_row_dev, const int32_t* dst_rank_dev, const uint64_t* peer_base_dev,
+                  int64_t dst_offset_doubles, void* stream);
 /* this rank's share of 2 * <bra|G_j|ket> summed by parameter; the caller adds the shares (all-reduce) */
 int tcc_shard_gradient(tcc_plan* plan, double* grad_host /* [num_params] */, void* stream);
 /* Contributions to sigma = H c of the storage rows [row_lo, row_lo + row_cnt): same-spin terms of these rows and

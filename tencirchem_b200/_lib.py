@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtcc_b200.so")
+# TCC_B200_LIB_NAME: another build of the SAME library in tencirchem_b200/lib (kernel experiments with other compile flags)
+LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("TCC_B200_LIB_NAME", "libtcc_b200.so"))
 
 TCC_OK = 0
 TCC_ERR_TOO_MANY_QUBITS = -1
@@ -66,6 +67,9 @@ SIGNATURES = {
     "tcc_shard_forward": (C.c_int, [_p, C.c_int, _p, _p]),
     "tcc_shard_reverse": (C.c_int, [_p, C.c_int, _p, _p, _p]),
     "tcc_shard_reverse_strided": (C.c_int, [_p, C.c_int, _p, _p, C.c_int64, _p]),
+    "tcc_shard_reverse_interleaved": (C.c_int, [_p, C.c_int, _p, _p]),
+    "tcc_shard_can_interleave": (C.c_int, [_p]),
+    "tcc_push_rows": (C.c_int, [C.c_int, _p, C.c_int64, C.c_int64, _p, _p, _p, _p, C.c_int64, _p]),
     "tcc_shard_gradient": (C.c_int, [_p, _dp, _p]),
     "tcc_apply_h_rows": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, _p]),
     "tcc_shard_sigma_layouts": (C.c_int, [_p, _ip]),

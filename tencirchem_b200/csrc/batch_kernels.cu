@@ -348,6 +348,353 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
     }
 }
 
+// ================================================================================================================
+// Lean batch kernels (batches with active orbitals on both sides).  Same tiles, same arithmetic and the same order of
+// excitations as batch_kernel above; what changes is the work per excitation OUTSIDE the rotation itself:
+//   * the pairs come from a per-thread stream (Batch::stream8 / stream16): thread `lid` of a sub-block applies entry
+//     [slot * tps + lid] of each of the excitation's `slots` rounds -- no per-thread count tests, no offset arithmetic;
+//   * the excitation record in shared memory is 16 bytes (cos, sin with the tile's spectator sign folded in) read by
+//     one broadcast 128-bit load, plus 8 bytes (stream offset, slots) read only by the prefetch;
+//   * NV == 3: ket and bra are INTERLEAVED element by element ((ket, bra) = one 16-byte element) in HBM and in shared
+//     memory: one 128-bit gather / scatter per element and one 128-bit shared-memory access per pair end instead of
+//     two 64-bit ones; NV == 2 keeps them in two vectors (needed where no memory is left for an interleaved copy);
+//   * the four gradient partials of a prefetch group are reduced over the warp by a transposed butterfly (12 shuffles
+//     instead of 40).
+// ================================================================================================================
+constexpr int LK_DEPTH = 4;
+constexpr uint32_t LK_VALID = 0x80000000u;
+#ifndef LK_FWD_MINB
+#define LK_FWD_MINB 4  // resident CTAs per SM the forward kernel is compiled for (register cap 65536 / (256 * MINB))
+#endif
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = unsigned(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ double2 lds128(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ uint2 lds64u(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32u(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double flip_sign(double v, uint32_t flip) {
+    return __hiloint2double(__double2hiint(v) ^ int(flip), __double2loint(v));
+}
+
+template <int NV>
+__global__ void __launch_bounds__(BK_THREADS, NV == 1 ? LK_FWD_MINB : 2)
+lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, BatchDev bd, const double2* __restrict__ rot,
+                  double* __restrict__ partials, int n_tiles, SetStrides ss, TileRect rect) {
+    constexpr int NVEC = NV == 1 ? 1 : 2;        // vectors rotated
+    constexpr int ELW = NV == 3 ? 16 : 8;        // bytes of a tile element in shared memory
+    constexpr int ESH = NV == 3 ? 4 : 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    v0 += int64_t(blockIdx.y) * ss.vec;
+    if (NV == 2) v1 += int64_t(blockIdx.y) * ss.vec;
+    rot += int64_t(blockIdx.y) * ss.rot;
+    if (NVEC == 2) partials += int64_t(blockIdx.y) * ss.part;
+    const int pa_loc = blockIdx.x / rect.pb_cnt;
+    const int pa_id = rect.pa_lo + pa_loc;
+    const int pb_id = rect.pb_lo + (blockIdx.x - pa_loc * rect.pb_cnt);
+    const int tile_id = pa_id * bd.B.n_panels + pb_id;
+    const PanelDesc pa = bd.A.panels[pa_id];
+    const PanelDesc pb = bd.B.panels[pb_id];
+    const int nR = int(pa.G) * int(pa.c), nC = int(pb.G) * int(pb.c);
+    const int ld = int(pb.ld);
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const int nops = bd.nops;
+    // shared memory: tile(s) | records [nops] (cos, sin) | warp partials [nops][nwarps] | meta [nops] (offset, slots) |
+    // spectator masks [nops] | row addresses [nR]
+    const size_t tile_bytes = (size_t(nR) * ld * ELW + 15) & ~size_t(15);
+    unsigned char* t0 = smem_raw;
+    unsigned char* t1 = t0 + (NV == 2 ? tile_bytes : 0);
+    double2* recs = reinterpret_cast<double2*>(t1 + tile_bytes);
+    double* wpart = reinterpret_cast<double*>(recs + nops);
+    uint2* metas = reinterpret_cast<uint2*>(wpart + (NVEC == 2 ? size_t(nops) * nwarps : 0));
+    uint32_t* smasks = reinterpret_cast<uint32_t*>(metas + nops);
+    uint32_t* row_addr = smasks + nops;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t* addr_a = bd.A.addr + pa.off;
+    const uint32_t* cols_sorted = bd.B.addr_sorted + pb.off;
+    const uint16_t* ord_b = bd.B.ord + pb.off;
+    for (int i = tid; i < nR; i += nthreads) row_addr[i] = __ldg(addr_a + i);
+    int64_t colg[BK_COLCH];
+    int lcs[BK_COLCH];
+    const bool reg_cols = nC <= 32 * BK_COLCH;
+#pragma unroll
+    for (int j = 0; j < BK_COLCH; ++j) {
+        const int t = lane + 32 * j;
+        colg[j] = 0;
+        lcs[j] = -1;
+        if (reg_cols && t < nC) {
+            colg[j] = __ldg(cols_sorted + t);
+            lcs[j] = __ldg(ord_b + t);
+        }
+    }
+    // sub-blocks on the NOMINAL class grid of the panel pair (the streams are laid out for it); a last, partly filled
+    // panel leaves the threads of its missing classes idle
+    const int Gan = max(1, int(pa.Gn)), Gbn = max(1, int(pb.Gn));
+    const int nsub = Gan * Gbn;
+    const int tps = nthreads / nsub;
+    const int sub = tid / tps;
+    const int ga = sub / Gbn, gb = sub - ga * Gbn;
+    const bool active = sub < nsub && ga < int(pa.G) && gb < int(pb.G);
+    const int lid = tid - sub * tps;
+    const int sbase = active ? ga * int(pa.c) * ld + gb * int(pb.c) : 0;
+    const int sshift_a = ga, sshift_b = 16 + gb;
+    const bool multi = nsub > 1;
+
+    auto setup_ops = [&]() {
+        for (int t = tid; t < nops; t += nthreads) {
+            const BatchOp op = bd.ops[t];
+            const int fwd_pos = bd.reversed ? nops - 1 - t : t;
+            const int* si = bd.stream_index + ((size_t(fwd_pos) * (bd.A.m + 1) + int(pa.e)) * (bd.B.m + 1) + int(pb.e)) * 2;
+            metas[t] = make_uint2(uint32_t(si[0]), uint32_t(si[1]));
+            uint32_t smask = 0;
+            if (op.h_a >= 0)
+                for (int g = 0; g < int(pa.G); ++g) smask |= (uint32_t(__popc(bd.A.sigma[pa.class_off + g] & op.zspec_a)) & 1u) << g;
+            if (op.h_b >= 0)
+                for (int g = 0; g < int(pb.G); ++g) smask |= (uint32_t(__popc(bd.B.sigma[pb.class_off + g] & op.zspec_b)) & 1u) << (16 + g);
+            const double2 cs = __ldg(rot + op.op_index);
+            // one class per side: the spectator sign of the tile is folded into the sine
+            const bool fold = !multi && (((smask ^ (smask >> 16)) & 1u) != 0);
+            recs[t] = make_double2(cs.x, fold ? -cs.y : cs.y);
+            smasks[t] = smask;
+        }
+    };
+    __syncthreads();  // row_addr
+    // ---- gather the tile (asynchronous copies: every element is in flight before the first wait)
+    if (reg_cols) {
+        for (int lr = warp; lr < nR; lr += nwarps) {
+            const int64_t ra = int64_t(row_addr[lr]) * nb;
+#pragma unroll
+            for (int j = 0; j < BK_COLCH; ++j)
+                if (lcs[j] >= 0) {
+                    if (NV == 3) {
+                        cp_async16(t0 + (size_t(lr) * ld + lcs[j]) * 16, v0 + (ra + colg[j]) * 2);
+                    } else {
+                        cp_async8(reinterpret_cast<double*>(t0) + lr * ld + lcs[j], v0 + ra + colg[j]);
+                        if (NV == 2) cp_async8(reinterpret_cast<double*>(t1) + lr * ld + lcs[j], v1 + ra + colg[j]);
+                    }
+                }
+        }
+        setup_ops();
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    } else {
+        setup_ops();
+        for (int lr = warp; lr < nR; lr += nwarps) {
+            const int64_t row = int64_t(row_addr[lr]) * nb;
+            for (int t = lane; t < nC; t += 32) {
+                const int lc = __ldg(ord_b + t);
+                const int64_t g = row + __ldg(cols_sorted + t);
+                if (NV == 3) {
+                    reinterpret_cast<double2*>(t0)[lr * ld + lc] = reinterpret_cast<const double2*>(v0)[g];
+                } else {
+                    reinterpret_cast<double*>(t0)[lr * ld + lc] = v0[g];
+                    if (NV == 2) reinterpret_cast<double*>(t1)[lr * ld + lc] = v1[g];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- the excitations of the batch, in order
+    {
+        const uint32_t* __restrict__ sp = (NV == 3 ? bd.stream16 : bd.stream8) + lid;
+        const uint32_t sh0 = uint32_t(__cvta_generic_to_shared(t0)) + (uint32_t(sbase) << ESH);
+        const uint32_t sh1 = uint32_t(__cvta_generic_to_shared(t1)) + (uint32_t(sbase) << ESH);
+        const uint32_t rec_s = uint32_t(__cvta_generic_to_shared(recs));
+        const uint32_t meta_s = uint32_t(__cvta_generic_to_shared(metas));
+        const uint32_t mask_s = uint32_t(__cvta_generic_to_shared(smasks));
+        uint32_t cur0[LK_DEPTH], cur1[LK_DEPTH], nxt0[LK_DEPTH], nxt1[LK_DEPTH];
+        double accs[LK_DEPTH];
+        auto fetch = [&](int tbase, uint32_t* e0, uint32_t* e1) {
+#pragma unroll
+            for (int j = 0; j < LK_DEPTH; ++j) {
+                const int t = tbase + j;
+                e0[j] = 0;
+                e1[j] = 0;
+                if (t < nops && active) {
+                    const uint2 m = lds64u(meta_s + t * 8);
+                    if (m.y > 0) e0[j] = __ldg(sp + m.x);
+                    if (m.y > 1) e1[j] = __ldg(sp + m.x + tps);
+                }
+            }
+        };
+        // flip = sign of the pair (bit 30 of the entry) x spectator sign of the sub-block (packed tiles only), as an FP64
+        // sign bit XORed into the sine and into the gradient term: no FP64 negate / select
+        auto pair = [&](uint32_t e, double cs, double sn, uint32_t sflip, double& acc) {
+            const uint32_t flip = ((e << 1) & 0x80000000u) ^ sflip;
+            const double p = flip_sign(sn, flip);
+            if (NV == 3) {
+                const uint32_t o1 = (e & 0x7fffu) << 4, o2 = (e >> 11) & 0x7fff0u;
+                const double2 a = lds128(sh0 + o1), b = lds128(sh0 + o2);  // (ket, bra) of either end
+                // <bra|G|ket> of the pair is invariant under the common rotation: taken from the values before it
+                acc = fma(flip_sign(a.y, flip), b.x, acc);
+                acc = fma(-flip_sign(b.y, flip), a.x, acc);
+                sts128(sh0 + o1, cs * a.x + p * b.x, cs * a.y + p * b.y);
+                sts128(sh0 + o2, cs * b.x - p * a.x, cs * b.y - p * a.y);
+            } else {
+                const uint32_t o1 = (e & 0x7fffu) << 3, o2 = (e >> 12) & 0x3fff8u;
+                const double x = lds64(sh0 + o1), y = lds64(sh0 + o2);
+                if (NV == 2) {
+                    const double bx = lds64(sh1 + o1), by = lds64(sh1 + o2);
+                    acc = fma(flip_sign(bx, flip), y, acc);
+                    acc = fma(-flip_sign(by, flip), x, acc);
+                    sts64(sh1 + o1, cs * bx + p * by);
+                    sts64(sh1 + o2, cs * by - p * bx);
+                }
+                sts64(sh0 + o1, cs * x + p * y);
+                sts64(sh0 + o2, cs * y - p * x);
+            }
+        };
+        fetch(0, cur0, cur1);
+        for (int tb = 0; tb < nops; tb += LK_DEPTH) {
+            fetch(tb + LK_DEPTH, nxt0, nxt1);
+#pragma unroll
+            for (int j = 0; j < LK_DEPTH; ++j) {
+                const int t = tb + j;
+                accs[j] = 0.0;
+                if (t < nops) {
+                    const uint32_t e0 = cur0[j], e1 = cur1[j];
+                    if (e0 & LK_VALID) {  // an entry in round 1 implies one in round 0
+                        const double2 r = lds128(rec_s + t * 16);
+                        const double sn = r.y;
+                        uint32_t sflip = 0;
+                        if (multi) {
+                            const uint32_t sm = lds32u(mask_s + t * 4);
+                            sflip = ((sm >> sshift_a) ^ (sm >> sshift_b)) << 31;
+                        }
+                        double acc = 0.0;
+                        pair(e0, r.x, sn, sflip, acc);
+                        if (e1 & LK_VALID) {
+                            pair(e1, r.x, sn, sflip, acc);
+                            const uint2 m = lds64u(meta_s + t * 8);
+                            for (uint32_t s_ = 2; s_ < m.y; ++s_) {
+                                const uint32_t e = __ldg(sp + m.x + s_ * tps);
+                                if (e & LK_VALID) pair(e, r.x, sn, sflip, acc);
+                            }
+                        }
+                        accs[j] = acc;
+                    }
+                    __syncthreads();
+                }
+            }
+            if (NVEC == 2) {
+                // transposed butterfly: after two exchange steps every lane holds ONE partial of ONE excitation of the
+                // group (excitation 2 * bit4(lane) + bit3(lane)); three plain steps finish the sum
+                static_assert(LK_DEPTH == 4, "the reduction below is written for groups of four");
+                const bool hi16 = lane & 16, hi8 = lane & 8;
+                const double s0 = hi16 ? accs[0] : accs[2], s1 = hi16 ? accs[1] : accs[3];
+                double k0 = (hi16 ? accs[2] : accs[0]) + __shfl_xor_sync(0xffffffffu, s0, 16);
+                double k1 = (hi16 ? accs[3] : accs[1]) + __shfl_xor_sync(0xffffffffu, s1, 16);
+                double k = (hi8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+                k += __shfl_xor_sync(0xffffffffu, k, 4);
+                k += __shfl_xor_sync(0xffffffffu, k, 2);
+                k += __shfl_xor_sync(0xffffffffu, k, 1);
+                if ((lane & 7) == 0) {
+                    const int j = ((lane >> 4) << 1) | ((lane >> 3) & 1);
+                    if (tb + j < nops) wpart[(tb + j) * nwarps + warp] = k;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < LK_DEPTH; ++j) {
+                cur0[j] = nxt0[j];
+                cur1[j] = nxt1[j];
+            }
+        }
+    }
+
+    // ---- scatter the tile back
+    if (reg_cols) {
+        for (int lr = warp; lr < nR; lr += nwarps) {
+            const int64_t ra = int64_t(row_addr[lr]) * nb;
+#pragma unroll
+            for (int j = 0; j < BK_COLCH; ++j)
+                if (lcs[j] >= 0) {
+                    if (NV == 3) {
+                        reinterpret_cast<double2*>(v0)[ra + colg[j]] = reinterpret_cast<const double2*>(t0)[lr * ld + lcs[j]];
+                    } else {
+                        v0[ra + colg[j]] = reinterpret_cast<const double*>(t0)[lr * ld + lcs[j]];
+                        if (NV == 2) v1[ra + colg[j]] = reinterpret_cast<const double*>(t1)[lr * ld + lcs[j]];
+                    }
+                }
+        }
+    } else {
+        for (int lr = warp; lr < nR; lr += nwarps) {
+            const int64_t row = int64_t(row_addr[lr]) * nb;
+            for (int t = lane; t < nC; t += 32) {
+                const int lc = __ldg(ord_b + t);
+                const int64_t g = row + __ldg(cols_sorted + t);
+                if (NV == 3) {
+                    reinterpret_cast<double2*>(v0)[g] = reinterpret_cast<const double2*>(t0)[lr * ld + lc];
+                } else {
+                    v0[g] = reinterpret_cast<const double*>(t0)[lr * ld + lc];
+                    if (NV == 2) v1[g] = reinterpret_cast<const double*>(t1)[lr * ld + lc];
+                }
+            }
+        }
+    }
+    if (NVEC == 2) {
+        __syncthreads();
+        for (int t = tid; t < nops; t += nthreads) {
+            double s = 0.0;
+            for (int w = 0; w < nwarps; ++w) s += wpart[t * nwarps + w];
+            // one class per side: the tile's spectator sign was folded into the sine; the gradient term takes it here
+            if (!multi && (((smasks[t] ^ (smasks[t] >> 16)) & 1u) != 0)) s = -s;
+            partials[int64_t(t) * n_tiles + tile_id] = s;
+        }
+    }
+}
+
+size_t lean_smem_bytes(int max_rows, int max_cols, int nops, int nv) {
+    const size_t ld = size_t(max_cols) | 1;
+    const size_t elw = nv == 3 ? 16 : 8;
+    size_t bytes = ((size_t(max_rows) * ld * elw + 15) & ~size_t(15)) * (nv == 2 ? 2 : 1);
+    bytes += size_t(nops) * 16;                                // records
+    if (nv >= 2) bytes += size_t(nops) * BK_WARPS * sizeof(double);  // warp partials
+    bytes += size_t(nops) * 8 + size_t(nops) * 4;                 // meta, spectator masks
+    bytes += size_t(max_rows) * sizeof(uint32_t);
+    return bytes + 16;
+}
+
+// (ket, bra) <-> interleaved [N][2]
+__global__ void __launch_bounds__(256) interleave_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                         double2* __restrict__ out, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256) out[i] = make_double2(a[i], b[i]);
+}
+__global__ void __launch_bounds__(256) deinterleave_kernel(const double2* __restrict__ in, double* __restrict__ a,
+                                                           double* __restrict__ b, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256) {
+        const double2 v = in[i];
+        a[i] = v.x;
+        b[i] = v.y;
+    }
+}
+void launch_interleave(const double* a, const double* b, double* out, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    const unsigned blocks = unsigned(std::min<int64_t>((n + 255) / 256, 148 * 16));
+    interleave_kernel<<<blocks, 256, 0, st>>>(a, b, reinterpret_cast<double2*>(out), n);
+}
+void launch_deinterleave(const double* in, double* a, double* b, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    const unsigned blocks = unsigned(std::min<int64_t>((n + 255) / 256, 148 * 16));
+    deinterleave_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const double2*>(in), a, b, n);
+}
+
 // grad_ops[op_index] = s0 * sum over tiles of partials[t, :], fixed order
 __global__ void __launch_bounds__(256) batch_grad_reduce_kernel(const double* __restrict__ partials, int n_tiles,
                                                                 const BatchOp* __restrict__ ops, double* __restrict__ grad_ops,
@@ -381,6 +728,9 @@ size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv) {
 cudaError_t batch_kernels_configure() {
     cudaError_t e = cudaFuncSetAttribute(batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lean_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lean_batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lean_batch_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
@@ -441,7 +791,10 @@ void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const doubl
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
         if (grid.x == 0) return;  // a rank of a sharded plan may own no class of this batch
-        batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss, r);
+        if (bd.lean)
+            lean_batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss, r);
+        else
+            batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss, r);
     });
 }
 
@@ -452,7 +805,22 @@ void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& 
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
         if (grid.x == 0) return;
-        batch_kernel<2><<<grid, threads, r.smem_rev, s>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss, r);
+        if (bd.lean)
+            lean_batch_kernel<2><<<grid, threads, r.smem_rev, s>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss, r);
+        else
+            batch_kernel<2><<<grid, threads, r.smem_rev, s>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss, r);
+    });
+    batch_grad_reduce_kernel<<<dim3(bd.nops, unsigned(n_sets), 1), 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops, ss);
+}
+
+// reverse sweep of one batch on interleaved (ket, bra) elements: kb = [rows][nb][2]
+void launch_batch_reverse_il(double* kb, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
+                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan) {
+    const int n_tiles = bd.B.n_panels * bd.A.n_panels;
+    fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
+        dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
+        if (grid.x == 0) return;
+        lean_batch_kernel<3><<<grid, threads, r.smem_il, s>>>(kb, nullptr, nb, bd, rot, partials, n_tiles, ss, r);
     });
     batch_grad_reduce_kernel<<<dim3(bd.nops, unsigned(n_sets), 1), 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops, ss);
 }

@@ -27,6 +27,10 @@ struct BatchDev {
     const BatchOp* ops;  // application order for this direction
     const uint32_t* plist;
     const int32_t* plist_index;  // indexed by the FORWARD position of the op in the batch
+    const uint32_t* stream8;     // lean per-thread streams (Batch::stream8 / stream16), null without `lean`
+    const uint32_t* stream16;
+    const int32_t* stream_index;
+    int lean;                    // the batch runs on lean_batch_kernel
     int nops;
     int ld_fixed;
     int reversed;  // ops[] is the forward list reversed
@@ -44,6 +48,7 @@ struct SetStrides {
 struct TileRect {
     int pa_lo, pa_cnt, pb_lo, pb_cnt;
     size_t smem_fwd, smem_rev;
+    size_t smem_il;  // reverse sweep on interleaved (ket, bra) elements
 };
 
 // Auxiliary streams for the rectangle launches of one batch: the rectangles are independent sets of tiles, so they
@@ -58,6 +63,11 @@ struct StreamFan {
 
 cudaError_t batch_kernels_configure();
 size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv);
+size_t lean_smem_bytes(int max_rows, int max_cols, int nops, int nv);
+void launch_batch_reverse_il(double* kb, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
+                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan);
+void launch_interleave(const double* a, const double* b, double* out, int64_t n, cudaStream_t st);
+void launch_deinterleave(const double* in, double* a, double* b, int64_t n, cudaStream_t st);
 void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
                           int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan);
 void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot,

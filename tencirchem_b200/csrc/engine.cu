@@ -141,6 +141,9 @@ struct tcc_plan {
     double* bra = nullptr;
     double* ws1 = nullptr;
     double* ws2 = nullptr;
+    double* kb = nullptr;   // interleaved (ket, bra) elements of the reverse sweep, [N][2]
+    int lean = 1;           // lean per-thread streams for two-sided batches (TCC_B200_LEAN=0: the plain pair lists)
+    int rev_interleave = 1; // reverse sweep on interleaved (ket, bra) elements (TCC_B200_REV_IL=0: two vectors)
     double* io1 = nullptr;  // reference-order staging for the host-buffer entry points
     double* io2 = nullptr;
     double* partials = nullptr;
@@ -242,6 +245,15 @@ static int upload_batches(tcc_plan* p) {
         CUDA_TRY(dev_upload(p, hb.plist_index, &db.fwd.plist_index, &db.allocs));
         db.fwd.ld_fixed = hb.ld_fixed;
         db.fwd.reversed = 0;
+        db.fwd.stream8 = db.fwd.stream16 = nullptr;
+        db.fwd.stream_index = nullptr;
+        db.fwd.lean = 0;
+        if (p->lean && hb.lean_threads > 0 && hb.lean_threads == p->batch_threads && hb.lean_threads == p->batch_threads_rev) {
+            CUDA_TRY(dev_upload(p, hb.stream8, &db.fwd.stream8, &db.allocs));
+            CUDA_TRY(dev_upload(p, hb.stream16, &db.fwd.stream16, &db.allocs));
+            CUDA_TRY(dev_upload(p, hb.stream_index, &db.fwd.stream_index, &db.allocs));
+            db.fwd.lean = 1;
+        }
         db.rev = db.fwd;
         db.rev.reversed = 1;
         std::vector<BatchOp> rev_ops(hb.ops.rbegin(), hb.ops.rend());
@@ -295,8 +307,9 @@ static int upload_batches(tcc_plan* p) {
                     r.pb_cnt = xb[1];
                     // ld of a tile follows its beta panel except when the beta side has no active orbitals (fixed ld)
                     const int cols = hb.B.m > 0 ? xb[2] : hb.B.max_panel;
-                    r.smem_fwd = batch_smem_bytes(xa[2], cols, db.nops, 1);
-                    r.smem_rev = batch_smem_bytes(xa[2], cols, db.nops, 2);
+                    r.smem_fwd = db.fwd.lean ? lean_smem_bytes(xa[2], cols, db.nops, 1) : batch_smem_bytes(xa[2], cols, db.nops, 1);
+                    r.smem_rev = db.fwd.lean ? lean_smem_bytes(xa[2], cols, db.nops, 2) : batch_smem_bytes(xa[2], cols, db.nops, 2);
+                    r.smem_il = db.fwd.lean ? lean_smem_bytes(xa[2], cols, db.nops, 3) : 0;
                     db.smem_fwd = std::max(db.smem_fwd, r.smem_fwd);
                     db.smem_rev = std::max(db.smem_rev, r.smem_rev);
                     if (r.pa_cnt > 0 && r.pb_cnt > 0) out->push_back(r);
@@ -304,6 +317,7 @@ static int upload_batches(tcc_plan* p) {
         };
         make_rects(split >= 2, &db.rects);
         make_rects(split >= 1, &db.rects_rev);
+        for (const TileRect& r : db.rects_rev) db.smem_rev = std::max(db.smem_rev, r.smem_il);
         if (db.smem_rev > 232448)
             return fail(TCC_ERR_BAD_ARGUMENT, "batch tile does not fit in shared memory: lower TCC_B200_TILE_ELEMS");
         max_part = std::max(max_part, size_t(db.nops) * size_t(db.n_tiles));
@@ -419,8 +433,11 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
     p->batch_threads = std::min(256, std::max(32, env_int("TCC_B200_BATCH_THREADS", 256) / 32 * 32));
     p->batch_threads_rev = std::min(256, std::max(32, env_int("TCC_B200_BATCH_THREADS_REV", p->batch_threads) / 32 * 32));
     if (world > 1) p->mode = 0;  // sharded plans run the batched engine only
+    p->lean = env_int("TCC_B200_LEAN", 1) != 0 && p->batch_threads == p->batch_threads_rev && (p->batch_threads & (p->batch_threads - 1)) == 0 &&
+              p->batch_threads >= 64;
+    p->rev_interleave = p->lean && env_int("TCC_B200_REV_IL", 1) != 0;
     p->hp.error.clear();
-    p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0, rank, world);
+    p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0, rank, world, p->lean ? p->batch_threads : 0);
     if (!p->hp.error.empty()) {
         g_error = p->hp.error;
         delete p;
@@ -512,6 +529,7 @@ void tcc_plan_destroy(tcc_plan* p) {
     cudaFree(p->bra);
     cudaFree(p->ws1);
     cudaFree(p->ws2);
+    cudaFree(p->kb);
     cudaFree(p->io1);
     cudaFree(p->io2);
     cudaFree(p->partials);
@@ -813,11 +831,46 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
         // d_rot_rev was uploaded together with d_rot_fwd by the forward sweep of the same parameters
         p->prof.mark(TCC_PROF_REV_BATCH, st);
         const int nbt = int(p->dbatches.size());
+        // Interleaved mode: (ket, bra) become one 16-byte element per determinant for the whole sweep (one pass to
+        // build it; nothing is converted back -- only the gradients leave the sweep).  Batches without lean streams
+        // (a side without active orbitals) work on the two vectors: the data is converted around them.
+        bool use_il = p->rev_interleave != 0;
+        if (use_il) {
+            bool any = false;
+            for (auto& db : p->dbatches) any = any || db.rev.lean;
+            use_il = any;
+        }
+        if (use_il && !p->kb) {
+            double* kb = nullptr;
+            if (cudaMalloc(&kb, sizeof(double) * 2 * size_t(hp.N)) == cudaSuccess) {
+                p->kb = kb;
+                p->dev_bytes += int64_t(sizeof(double)) * 2 * hp.N;
+            } else {
+                cudaGetLastError();  // no memory for the interleaved copy: sweep on the two vectors
+                use_il = false;
+            }
+        }
+        bool in_kb = false;
         for (int b = nbt - 1; b >= 0; --b) {
             BatchDevSet& db = p->dbatches[b];
             if (p->btimer.on) cudaEventRecord(p->btimer.ev[nbt + 1 + (nbt - 1 - b)], st);
-            launch_batch_reverse(ket, bra, hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
-                                 SetStrides{0, 0, 0, 0}, st, &p->fan);
+            if (use_il && db.rev.lean) {
+                if (!in_kb) {
+                    launch_interleave(ket, bra, p->kb, hp.N, st);
+                    p->launches += 1;
+                    in_kb = true;
+                }
+                launch_batch_reverse_il(p->kb, hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
+                                        SetStrides{0, 0, 0, 0}, st, &p->fan);
+            } else {
+                if (in_kb) {
+                    launch_deinterleave(p->kb, ket, bra, hp.N, st);
+                    p->launches += 1;
+                    in_kb = false;
+                }
+                launch_batch_reverse(ket, bra, hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
+                                     SetStrides{0, 0, 0, 0}, st, &p->fan);
+            }
             p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * hp.N);  // the tiny gradient-reduce launch rides along
             p->launches += 2;
         }
@@ -1249,6 +1302,37 @@ int tcc_shard_reverse_strided(tcc_plan* p, int seg, double* ket_local_dev, doubl
     return 0;
 }
 
+// reverse sweep of a segment on ONE block of interleaved elements: kb_local = [local rows][nb][2] with (ket, bra) of a
+// determinant next to each other (16-byte elements: one row move, one gather per element, one shared-memory access per
+// pair end).  Returns TCC_ERR_BAD_ARGUMENT when a batch of the segment has no lean streams (use the two-vector call).
+int tcc_shard_reverse_interleaved(tcc_plan* p, int seg, double* kb_local_dev, void* stream) {
+    if (!p || !kb_local_dev || seg < 0 || seg >= int(p->hp.segments.size())) return fail(TCC_ERR_BAD_ARGUMENT, "bad argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    cudaStream_t st = cudaStream_t(stream);
+    const Segment& s = p->hp.segments[seg];
+    for (int b = s.batch_lo; b < s.batch_hi; ++b)
+        if (!p->dbatches[b].rev.lean) return fail(TCC_ERR_BAD_ARGUMENT, "segment holds a batch without lean streams");
+    p->prof.mark(TCC_PROF_REV_BATCH, st);
+    for (int b = s.batch_hi - 1; b >= s.batch_lo; --b) {
+        BatchDevSet& db = p->dbatches[b];
+        launch_batch_reverse_il(kb_local_dev, p->hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
+                                SetStrides{0, 0, 0, 0}, st, &p->fan);
+        p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
+        p->launches += 2;
+    }
+    p->prof.mark(-1, st);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// 1 when every batch of the plan can run the interleaved reverse sweep (tcc_shard_reverse_interleaved)
+int tcc_shard_can_interleave(const tcc_plan* p) {
+    if (!p || !p->rev_interleave || p->device < 0) return 0;
+    for (const auto& db : p->dbatches)
+        if (!db.rev.lean) return 0;
+    return 1;
+}
+
 int tcc_shard_reverse(tcc_plan* p, int seg, double* ket_local_dev, double* bra_local_dev, void* stream) {
     return tcc_shard_reverse_strided(p, seg, ket_local_dev, bra_local_dev, p ? p->hp.nb : 0, stream);
 }
@@ -1393,6 +1477,21 @@ int tcc_shard_sigma_ab(tcc_plan* p, int pass, const double* c_local_dev, double*
     p->prof.count(TCC_PROF_SIGMA_AB, (rows + 65534) / 65535, 3 * 8 * rows * hp.nb);
     p->prof.mark(-1, st);
     p->launches += (rows + 65534) / 65535;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Row move over peer memory (no plan needed): see push_rows_kernel.  All pointers are device pointers of `device`;
+// peer_base_dev[q] = base address of rank q's destination block as mapped into this process.
+int tcc_push_rows(int device, const double* src_dev, int64_t row_doubles, int64_t n_rows, const int64_t* src_row_dev,
+                  const int64_t* dst_row_dev, const int32_t* dst_rank_dev, const uint64_t* peer_base_dev, int64_t dst_offset_doubles,
+                  void* stream) {
+    if (n_rows < 0 || row_doubles < 0 || dst_offset_doubles < 0) return fail(TCC_ERR_BAD_ARGUMENT, "negative size");
+    if (n_rows == 0 || row_doubles == 0) return 0;
+    if (!src_dev || !src_row_dev || !dst_row_dev || !dst_rank_dev || !peer_base_dev) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    launch_push_rows(src_dev, row_doubles, n_rows, src_row_dev, dst_row_dev, dst_rank_dev, peer_base_dev, dst_offset_doubles,
+                     cudaStream_t(stream));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

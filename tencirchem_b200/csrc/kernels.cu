@@ -6,6 +6,7 @@
 // the beta hop list; the sign of the matrix element G_IJ is s0 * sign_a * sign_b.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 
 #include "plan.hpp"
@@ -553,6 +554,47 @@ void launch_sigma_hcb(const double* c, double* sigma, int64_t nstr, const uint32
     (void)k;
     unsigned blocks = unsigned((nstr + 127) / 128);
     sigma_hcb_kernel<<<dim3(blocks, unsigned(n_sets), 1), 128, 0, st>>>(c, sigma, nstr, strings, n, diag1, hop, diag2, binom, binom_ld, bitpos);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Row move of the alpha-row sharded engine over peer memory: every local row goes straight to its new owner.
+//   dst(rank q)[dst_row[i], :] = src[src_row[i], :]   for the i-th moved row, q = dst_rank[i]
+// peer_base[q] is the base address of rank q's destination block as mapped INTO THIS process (NVLink peer mapping of a
+// symmetric allocation; for q == this rank the local address), so the copy is one pass of 16-byte stores over NVLink:
+// no pack buffer, no collective, no unpack pass.  grid.x = moved rows x pieces of a row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) push_rows_kernel(const double* __restrict__ src, int64_t row_doubles, int pieces,
+                                                        const int64_t* __restrict__ src_row, const int64_t* __restrict__ dst_row,
+                                                        const int32_t* __restrict__ dst_rank, const uint64_t* __restrict__ peer_base,
+                                                        int64_t dst_offset) {
+    const int64_t i = blockIdx.x / pieces;
+    const int piece = int(blockIdx.x - i * pieces);
+    const double* s = src + src_row[i] * row_doubles;
+    double* d = reinterpret_cast<double*>(peer_base[dst_rank[i]]) + dst_offset + dst_row[i] * row_doubles;
+    // piece boundaries in units of 2 doubles so that 16-byte accesses stay aligned whenever the rows are
+    const int64_t pairs = row_doubles >> 1;
+    const int64_t lo = (pairs * piece) / pieces, hi = (pairs * (piece + 1)) / pieces;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+        const double2* s2 = reinterpret_cast<const double2*>(s);
+        double2* d2 = reinterpret_cast<double2*>(d);
+        for (int64_t k = lo + threadIdx.x; k < hi; k += 256) d2[k] = s2[k];
+    } else {
+        for (int64_t k = 2 * lo + threadIdx.x; k < 2 * hi; k += 256) d[k] = s[k];
+    }
+    if ((row_doubles & 1) && piece == pieces - 1 && threadIdx.x == 0) d[row_doubles - 1] = s[row_doubles - 1];
+}
+
+void launch_push_rows(const double* src, int64_t row_doubles, int64_t n_rows, const int64_t* src_row, const int64_t* dst_row,
+                      const int32_t* dst_rank, const uint64_t* peer_base, int64_t dst_offset, cudaStream_t st) {
+    if (n_rows <= 0 || row_doubles <= 0) return;
+    // enough CTAs to fill the machine even for few long rows; a piece is at least 4 KB
+    int pieces = int(std::max<int64_t>(1, std::min<int64_t>((row_doubles * 8) / 4096, (148 * 16 + n_rows - 1) / n_rows)));
+    for (int64_t r0 = 0; r0 < n_rows; r0 += (int64_t(1) << 20)) {
+        const int64_t nr = std::min<int64_t>(n_rows - r0, int64_t(1) << 20);
+        push_rows_kernel<<<unsigned(nr * pieces), 256, 0, st>>>(src, row_doubles, pieces, src_row + r0, dst_row + r0, dst_rank + r0,
+                                                              peer_base, dst_offset);
+    }
 }
 
 }  // namespace tcc

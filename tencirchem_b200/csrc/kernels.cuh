@@ -47,6 +47,10 @@ void launch_sigma_hcb(const double* c, double* sigma, int64_t nstr, const uint32
                       const double* diag1, const double* hop, const double* diag2, const int64_t* binom,
                       int binom_ld, const int* bitpos, int n_sets, cudaStream_t st);
 
+// row move over peer memory: dst(rank dst_rank[i])[dst_row[i], :] = src[src_row[i], :] (kernels.cu)
+void launch_push_rows(const double* src, int64_t row_doubles, int64_t n_rows, const int64_t* src_row, const int64_t* dst_row,
+                      const int32_t* dst_rank, const uint64_t* peer_base, int64_t dst_offset, cudaStream_t st);
+
 // Gram matrix of the single-replacement intermediate D (rdm_kernels.cu); gram [n^2, n^2] must be zeroed; only the
 // blocks I <= J of the 64 x 64 block grid are written
 void launch_rdm_gram(const double* c, int64_t na, int64_t nb, const Link* links, int ml, int n, double* gram, int slices,

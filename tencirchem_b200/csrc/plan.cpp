@@ -393,6 +393,8 @@ void HostPlan::build_side(uint32_t S, int panel_target, SideBatch* side, bool si
             pd.c = uint16_t(csize);
             pd.e = uint16_t(e);
             pd.ld = uint16_t(side->ld_of_e[e]);
+            pd.Gn = uint16_t(m > 0 ? g_of_e[e] : 1);
+            pd.pad = 0;
             for (size_t q = p0; q < p1; ++q) {
                 side->sigma.push_back(cls_sigma[ids[q]]);
                 for (uint32_t a : members[ids[q]]) side->addr.push_back(a);
@@ -459,7 +461,37 @@ void HostPlan::active_sets(const std::vector<int>& group, int tile_elems, uint32
     *sb_out = sb;
 }
 
-void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch* out) {
+// order of the pairs of one excitation: groups of `group` consecutive entries (one shared-memory wavefront of the
+// access width in use) whose first elements fall into different banks, and likewise the second elements, as far as a
+// greedy search in a small window finds them.  The pairs of an excitation are independent, so any order is valid.
+static void bank_ordered(const std::vector<uint32_t>& raw, int group, std::vector<char>* taken, std::vector<uint32_t>* out) {
+    const uint32_t gm = uint32_t(group - 1);
+    taken->assign(raw.size(), 0);
+    size_t head = 0, emitted = 0;
+    while (emitted < raw.size()) {
+        uint32_t m1 = 0, m2 = 0;
+        for (int kk = 0; kk < group && emitted < raw.size(); ++kk) {
+            while (head < raw.size() && (*taken)[head]) ++head;
+            size_t pick = head;
+            const size_t lim = std::min(raw.size(), head + 96);
+            for (size_t c = head; c < lim; ++c) {
+                if ((*taken)[c]) continue;
+                const uint32_t b1 = 1u << (raw[c] & gm), b2 = 1u << ((raw[c] >> 15) & gm);
+                if (!(m1 & b1) && !(m2 & b2)) {
+                    pick = c;
+                    break;
+                }
+            }
+            (*taken)[pick] = 1;
+            m1 |= 1u << (raw[pick] & gm);
+            m2 |= 1u << ((raw[pick] >> 15) & gm);
+            out->push_back(raw[pick]);
+            ++emitted;
+        }
+    }
+}
+
+void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch* out, int lean_threads) {
     const uint32_t sa = out->sa, sb = out->sb;  // set by finalize (active_sets)
     int64_t ca = max_class(hcb ? 0 : popc(sa)), cb = max_class(popc(sb));
     int64_t pa = ca, pb = cb;
@@ -574,6 +606,15 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
     std::vector<Ent> ea_list, eb_list;
     std::vector<uint32_t> raw;
     std::vector<char> taken;
+    // lean streams: only for batches with active orbitals on both sides (the repeat path keeps the plain lists)
+    const bool lean = lean_threads > 0 && ma > 0 && mb > 0;
+    out->lean_threads = lean ? lean_threads : 0;
+    out->stream8.clear();
+    out->stream16.clear();
+    out->stream_index.assign(lean ? out->plist_index.size() : 0, 0);
+    std::vector<int> ga_nom(ma + 1, 1), gb_nom(mb + 1, 1);
+    for (const auto& pd : out->A.panels) ga_nom[pd.e] = std::max<int>(1, pd.Gn);
+    for (const auto& pd : out->B.panels) gb_nom[pd.e] = std::max<int>(1, pd.Gn);
     const bool bank_order = std::getenv("TCC_B200_BANK_ORDER") ? std::atoi(std::getenv("TCC_B200_BANK_ORDER")) != 0 : true;
     for (size_t t = 0; t < out->ops.size(); ++t) {
         const BatchOp& bo = out->ops[t];
@@ -591,36 +632,26 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
                 for (const Ent& a : ea_list)
                     for (const Ent& b : eb_list)
                         raw.push_back((a.s * ld + b.s) | ((a.d * ld + b.d) << 15) | ((a.sg ^ b.sg) << 30));
-                if (bank_order && raw.size() > 16) {
-                    // The pairs of one excitation are independent, so their order is free: emit them in groups of
-                    // 16 consecutive entries (one shared-memory wavefront of a 64-bit access) whose first elements
-                    // fall into different 8-byte banks, and likewise the second elements, as far as a greedy
-                    // search in a small window finds them.
-                    taken.assign(raw.size(), 0);
-                    size_t head = 0, emitted = 0;
-                    while (emitted < raw.size()) {
-                        uint32_t m1 = 0, m2 = 0;
-                        for (int kk = 0; kk < 16 && emitted < raw.size(); ++kk) {
-                            while (head < raw.size() && taken[head]) ++head;
-                            size_t pick = head;
-                            const size_t lim = std::min(raw.size(), head + 96);
-                            for (size_t c = head; c < lim; ++c) {
-                                if (taken[c]) continue;
-                                const uint32_t b1 = 1u << (raw[c] & 15u), b2 = 1u << ((raw[c] >> 15) & 15u);
-                                if (!(m1 & b1) && !(m2 & b2)) {
-                                    pick = c;
-                                    break;
-                                }
-                            }
-                            taken[pick] = 1;
-                            m1 |= 1u << (raw[pick] & 15u);
-                            m2 |= 1u << ((raw[pick] >> 15) & 15u);
-                            out->plist.push_back(raw[pick]);
-                            ++emitted;
-                        }
-                    }
-                } else {
+                if (bank_order && raw.size() > 16)
+                    bank_ordered(raw, 16, &taken, &out->plist);
+                else
                     out->plist.insert(out->plist.end(), raw.begin(), raw.end());
+                if (lean) {
+                    // per-thread stream of the class pair: `slots` rounds of tps entries, padded with invalid entries
+                    const int tps = std::max(1, lean_threads / (ga_nom[ea] * gb_nom[eb]));
+                    const int slots = int((raw.size() + tps - 1) / tps);
+                    out->stream_index[slot] = int32_t(out->stream8.size());
+                    out->stream_index[slot + 1] = slots;
+                    for (int width = 0; width < 2; ++width) {
+                        std::vector<uint32_t>& dst = width == 0 ? out->stream8 : out->stream16;
+                        const size_t before = dst.size();
+                        if (bank_order && raw.size() > 8)
+                            bank_ordered(raw, width == 0 ? 16 : 8, &taken, &dst);
+                        else
+                            dst.insert(dst.end(), raw.begin(), raw.end());
+                        for (size_t i = before; i < dst.size(); ++i) dst[i] |= 0x80000000u;
+                        dst.resize(before + size_t(slots) * tps, 0u);
+                    }
                 }
             }
         }
@@ -757,7 +788,7 @@ void HostPlan::build_sigma_pass_links() {
     }
 }
 
-void HostPlan::finalize(int tile_elems, bool use_layout, int rank, int world) {
+void HostPlan::finalize(int tile_elems, bool use_layout, int rank, int world, int lean_threads) {
     tile_elems = std::max(tile_elems, 64);
     shard_rank = rank;
     shard_world = world;
@@ -773,7 +804,7 @@ void HostPlan::finalize(int tile_elems, bool use_layout, int rank, int world) {
     batches.resize(groups.size());
     for (size_t g = 0; g < groups.size(); ++g) active_sets(groups[g], tile_elems, &batches[g].sa, &batches[g].sb);
     choose_row_layouts();
-    for (size_t g = 0; g < groups.size(); ++g) build_batch(groups[g], tile_elems, &batches[g]);
+    for (size_t g = 0; g < groups.size(); ++g) build_batch(groups[g], tile_elems, &batches[g], lean_threads);
 }
 
 void HostPlan::build_links() {

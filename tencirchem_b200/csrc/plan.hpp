@@ -60,6 +60,8 @@ struct PanelDesc {
     uint16_t c;          // strings per class
     uint16_t e;          // active electrons per class
     uint16_t ld;         // leading dimension of a tile whose columns are this panel: (full G * c) | 1
+    uint16_t Gn;         // nominal classes per panel of this electron count (G < Gn only in a last, partly filled panel)
+    uint16_t pad;
 };
 
 struct LocalHop {
@@ -98,6 +100,15 @@ struct Batch {
     // A side without active orbitals is not expanded: the kernel repeats the list over its rows / columns.
     std::vector<uint32_t> plist;
     std::vector<int32_t> plist_index;  // [n_ops][m_a + 1][m_b + 1][2] = (offset, count)
+    // Lean per-thread streams (batches with active orbitals on both sides): the pairs of excitation t in a tile of class
+    // pair (e_a, e_b) laid out as `slots` rounds of `tps` entries, tps = threads / (Gn_a * Gn_b) = threads of one
+    // (alpha class, beta class) sub-block; thread `lid` of the sub-block applies entry [slot * tps + lid] of every slot.
+    // Entry = i1 | i2 << 15 | sign << 30 | valid << 31.  Two orderings of the same pairs: `stream8` groups 16
+    // consecutive entries on distinct 8-byte banks (forward sweep and the two-vector reverse sweep), `stream16` groups
+    // 8 consecutive entries on distinct 16-byte banks (reverse sweep on interleaved (ket, bra) elements).
+    std::vector<uint32_t> stream8, stream16;
+    std::vector<int32_t> stream_index;  // [n_ops][m_a + 1][m_b + 1][2] = (offset, slots)
+    int lean_threads = 0;               // block size the streams were laid out for (0 = no streams)
     int ld_fixed = 0;                  // tile leading dimension when the beta side has no active orbitals
     uint32_t sa = 0, sb = 0;           // padded active sets
     int layout = 0;                    // row distribution the batch runs in (sharded plans)
@@ -157,7 +168,7 @@ struct HostPlan {
     int parse_op(const int32_t* idx, int len, int param, OpDesc* op);
     // groups ops into batches (orbital sets only), picks the storage order, builds strings, hop tables
     // and batch descriptors.  tile_elems = max determinants per on-chip tile.
-    void finalize(int tile_elems, bool use_layout, int rank = 0, int world = 1);
+    void finalize(int tile_elems, bool use_layout, int rank = 0, int world = 1, int lean_threads = 256);
     void attach_hops(OpDesc* op);
 
     uint32_t permute_bits(uint32_t s) const;
@@ -186,7 +197,7 @@ struct HostPlan {
     void build_strings();
     void active_sets(const std::vector<int>& group, int tile_elems, uint32_t* sa, uint32_t* sb) const;
     void choose_row_layouts();
-    void build_batch(const std::vector<int>& group, int tile_elems, Batch* out);
+    void build_batch(const std::vector<int>& group, int tile_elems, Batch* out, int lean_threads);
     void build_side(uint32_t S, int panel_target, SideBatch* side, bool single_string, bool pack_classes,
                     const RowLayout* rows);
     int64_t max_class(int m) const;

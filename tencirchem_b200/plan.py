@@ -151,6 +151,13 @@ class Plan:
         _lib.check(self.lib.tcc_shard_reverse_strided(self.handle, int(seg), C.c_void_p(ket_local.data_ptr()),
                                                       C.c_void_p(bra_local.data_ptr()), int(row_stride), self._stream()))
 
+    def shard_reverse_interleaved(self, seg: int, kb_local):
+        """kb_local: [local rows, nb, 2] block with (ket, bra) of every determinant side by side."""
+        _lib.check(self.lib.tcc_shard_reverse_interleaved(self.handle, int(seg), C.c_void_p(kb_local.data_ptr()), self._stream()))
+
+    def shard_can_interleave(self) -> bool:
+        return bool(self.lib.tcc_shard_can_interleave(self.handle))
+
     def shard_gradient(self) -> np.ndarray:
         g = np.zeros(max(self.n_params, 1), dtype=np.float64)
         _lib.check(self.lib.tcc_shard_gradient(self.handle, _dptr(g), self._stream()))

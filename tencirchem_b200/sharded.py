@@ -578,8 +578,11 @@ class ShardedUCC:
             total = t.cuda.get_device_properties(self.device).total_memory
             fuse = self.world > 1 and 2 * 8 * max(k_.numel() for k_ in kets) < total // 8
         if fuse:
+            # element-interleaved block [rows, nb, 2] when every batch has lean streams (16-byte elements in the kernel
+            # too), else row-interleaved [rows, 2, nb] (two vectors with a row stride)
+            il = all(st.plan.shard_can_interleave() for st in self.states)
             with self.timer.phase("reverse_interleave"):
-                both = [t.stack((kets[k], bras[k]), dim=1) for k in range(len(kets))]  # [rows, 2, nb]
+                both = [t.stack((kets[k], bras[k]), dim=2 if il else 1) for k in range(len(kets))]
             del kets, bras
             for seg in range(len(self.segments) - 1, -1, -1):
                 l = self.segments[seg][0]
@@ -587,7 +590,11 @@ class ShardedUCC:
                 layout = l
                 with self.timer.phase("reverse_kernels"):
                     for k, st in enumerate(self.states):
-                        if both[k].numel():
+                        if not both[k].numel():
+                            continue
+                        if il:
+                            st.plan.shard_reverse_interleaved(seg, both[k])
+                        else:
                             st.plan.shard_reverse_strided(seg, both[k][:, 0], both[k][:, 1], 2 * self.nb)
         else:
             for seg in range(len(self.segments) - 1, -1, -1):

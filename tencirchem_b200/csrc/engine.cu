@@ -143,6 +143,7 @@ struct tcc_plan {
     double* ws2 = nullptr;
     double* kb = nullptr;   // interleaved (ket, bra) elements of the reverse sweep, [N][2]
     int lean = 1;           // lean per-thread streams for two-sided batches (TCC_B200_LEAN=0: the plain pair lists)
+    int lean_fwd = 0;       // forward sweep on the lean kernel too (TCC_B200_LEAN_FWD=1); measured slower than batch_kernel<1>
     int rev_interleave = 1; // reverse sweep on interleaved (ket, bra) elements (TCC_B200_REV_IL=0: two vectors)
     double* io1 = nullptr;  // reference-order staging for the host-buffer entry points
     double* io2 = nullptr;
@@ -255,6 +256,7 @@ static int upload_batches(tcc_plan* p) {
             db.fwd.lean = 1;
         }
         db.rev = db.fwd;
+        db.fwd.lean = db.fwd.lean && p->lean_fwd;
         db.rev.reversed = 1;
         std::vector<BatchOp> rev_ops(hb.ops.rbegin(), hb.ops.rend());
         CUDA_TRY(dev_upload(p, hb.ops, &db.fwd.ops, &db.allocs));
@@ -308,8 +310,8 @@ static int upload_batches(tcc_plan* p) {
                     // ld of a tile follows its beta panel except when the beta side has no active orbitals (fixed ld)
                     const int cols = hb.B.m > 0 ? xb[2] : hb.B.max_panel;
                     r.smem_fwd = db.fwd.lean ? lean_smem_bytes(xa[2], cols, db.nops, 1) : batch_smem_bytes(xa[2], cols, db.nops, 1);
-                    r.smem_rev = db.fwd.lean ? lean_smem_bytes(xa[2], cols, db.nops, 2) : batch_smem_bytes(xa[2], cols, db.nops, 2);
-                    r.smem_il = db.fwd.lean ? lean_smem_bytes(xa[2], cols, db.nops, 3) : 0;
+                    r.smem_rev = db.rev.lean ? lean_smem_bytes(xa[2], cols, db.nops, 2) : batch_smem_bytes(xa[2], cols, db.nops, 2);
+                    r.smem_il = db.rev.lean ? lean_smem_bytes(xa[2], cols, db.nops, 3) : 0;
                     db.smem_fwd = std::max(db.smem_fwd, r.smem_fwd);
                     db.smem_rev = std::max(db.smem_rev, r.smem_rev);
                     if (r.pa_cnt > 0 && r.pb_cnt > 0) out->push_back(r);
@@ -436,6 +438,7 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
     p->lean = env_int("TCC_B200_LEAN", 1) != 0 && p->batch_threads == p->batch_threads_rev && (p->batch_threads & (p->batch_threads - 1)) == 0 &&
               p->batch_threads >= 64;
     p->rev_interleave = p->lean && env_int("TCC_B200_REV_IL", 1) != 0;
+    p->lean_fwd = p->lean && env_int("TCC_B200_LEAN_FWD", 0) != 0;
     p->hp.error.clear();
     p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0, rank, world, p->lean ? p->batch_threads : 0);
     if (!p->hp.error.empty()) {

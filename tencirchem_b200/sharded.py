@@ -88,9 +88,12 @@ class PhaseTimer:
 class LocalComm:
     """All ranks live in this process (virtual ranks on one device): collectives are local copies."""
 
-    def __init__(self, world: int):
+    def __init__(self, world: int, peer_memory: bool = True):
+        """peer_memory=False makes the row moves take the pack / exchange / unpack path of a transport without peer
+        mapping (test coverage of that path on one GPU)"""
         self.world = int(world)
         self.local_ranks = list(range(self.world))
+        self.peer_memory = bool(peer_memory)
 
     def exchange(self, send: List[List["torch.Tensor"]], recv_counts=None) -> List[List["torch.Tensor"]]:
         # send[i][d]: rows that local rank i sends to rank d  ->  recv[i][s]: rows rank i receives from rank s
@@ -108,6 +111,21 @@ class LocalComm:
             total += t
         for t in tensors:
             t.copy_(total)
+
+    def alloc_pool(self, n_doubles, device):
+        """-> (one flat float64 buffer per local rank, per local rank a device tensor [world] with the base address of
+        EVERY rank's buffer as seen from that rank, or None when peers are not addressable).  All virtual ranks share a
+        device: every buffer is directly addressable."""
+        import torch
+
+        bufs = [torch.empty(n_doubles, dtype=torch.float64, device=device) for _ in range(self.world)]
+        if not self.peer_memory:
+            return bufs, [None for _ in range(self.world)]
+        ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=device)
+        return bufs, [ptrs for _ in range(self.world)]
+
+    def stream_barrier(self):
+        """all ranks' streams have reached this point (virtual ranks share one stream: nothing to do)"""
 
     def all_gather_padded(self, blocks, max_rows):
         """blocks[i]: [rows_i, nb] of local rank i -> per local rank a [world, max_rows, nb] tensor whose slab s holds
@@ -134,13 +152,53 @@ class LocalComm:
 class TorchComm:
     """One rank per process over torch.distributed (NCCL on GPUs; gloo in the CPU tests)."""
 
-    def __init__(self):
+    def __init__(self, peer_memory="auto"):
+        """peer_memory: "auto" maps the shard pool of every rank into every process (CUDA symmetric memory over NVLink /
+        NVSwitch) when the backend is NCCL and the mapping succeeds, so that rows move by direct peer stores
+        (tcc_push_rows); "off" (and gloo, and a failed mapping) moves rows through NCCL all-to-all."""
         import torch.distributed as dist
 
         self.dist = dist
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
         self.local_ranks = [self.rank]
+        self.peer_memory = peer_memory
+        self._symm = None
+        self.peer_memory_error = None
+
+    def alloc_pool(self, n_doubles, device):
+        import os
+
+        import torch
+
+        want = self.peer_memory != "off" and self.dist.get_backend() == "nccl" and os.environ.get("TCC_B200_PEER_MEMORY", "1") != "0"
+        buf = hdl = None
+        if want:
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                buf = symm.empty(n_doubles, dtype=torch.float64, device=device)
+                hdl = symm.rendezvous(buf, self.dist.group.WORLD)
+            except Exception as exc:  # no peer mapping on this system: NCCL transport
+                self.peer_memory_error = repr(exc)
+                buf = hdl = None
+            # every rank must take the same path: if the mapping failed anywhere, nobody uses it
+            flag = torch.tensor([1.0 if hdl is not None else 0.0], device=device)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+            if float(flag[0]) < 1.0:
+                buf = hdl = None
+        if hdl is not None:
+            ptrs = torch.tensor([int(x) for x in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+            self._symm = hdl
+            return [buf], [ptrs]
+        self._symm = None
+        return [torch.empty(n_doubles, dtype=torch.float64, device=device)], [None]
+
+    def stream_barrier(self):
+        if self._symm is not None:
+            self._symm.barrier(channel=0)
+        else:
+            self.dist.barrier()
 
     def exchange(self, send, recv_counts):
         import torch
@@ -203,6 +261,78 @@ class TorchComm:
         return [x[self.rank].clone()]
 
 
+class ShardPool:
+    """Fixed pool of shard-sized buffers: every [rows, nb]-sized block of the sharded driver lives in one of `n_slots`
+    slots of ONE allocation per rank, made once.  Nothing shard-sized is allocated during an evaluation (at (20e,20o) on
+    8 GPUs four 33.5 GiB slots are all the memory there is), and because the allocation is symmetric -- same size and
+    slot offsets on every rank, mapped into every process when the transport allows it -- a row move writes straight
+    into slot s of the peers.  All ranks run the same program, so slot numbers agree across ranks."""
+
+    def __init__(self, comm, device, slot_doubles: int, n_slots: int):
+        import torch
+
+        self.torch = torch
+        self.comm = comm
+        self.slot = int(slot_doubles)
+        self.n_slots = int(n_slots)
+        self.buffers, self.peer_ptrs = comm.alloc_pool(self.slot * self.n_slots, device)
+        self.p2p = self.peer_ptrs[0] is not None
+        self._used = [False] * self.n_slots
+        self._owner = {}  # data_ptr of local rank 0's view -> (first slot, number of slots)
+
+    def reset(self):
+        self._used = [False] * self.n_slots
+        self._owner.clear()
+
+    def _take(self, n: int) -> int:
+        run = 0
+        for i in range(self.n_slots):
+            run = run + 1 if not self._used[i] else 0
+            if run == n:
+                first = i - n + 1
+                for j in range(first, i + 1):
+                    self._used[j] = True
+                return first
+        raise MemoryError(f"shard pool exhausted: {n} contiguous slot(s) of {self.n_slots} requested, in use {self._used}")
+
+    def empty(self, rows_per_rank, trailing):
+        """one block [rows_k, *trailing] per local rank, all in the same slot(s); `trailing` = (nb,) or (nb, 2) ..."""
+        per_row = int(np.prod(trailing))
+        need = max(int(r) for r in rows_per_rank) * per_row if len(rows_per_rank) else 0
+        n = max(1, -(-need // self.slot))
+        first = self._take(n)
+        out = []
+        for buf, r in zip(self.buffers, rows_per_rank):
+            out.append(buf[first * self.slot: first * self.slot + int(r) * per_row].view((int(r),) + tuple(trailing)))
+        self._owner[first * self.slot] = (first, n)
+        return out
+
+    def zeros(self, rows_per_rank, trailing):
+        out = self.empty(rows_per_rank, trailing)
+        for v in out:
+            v.zero_()
+        return out
+
+    def _key(self, vecs):
+        """storage offset of the block inside the pool buffer (None for blocks that live elsewhere)"""
+        if not vecs:
+            return None
+        v = vecs[0]
+        if v.untyped_storage().data_ptr() != self.buffers[0].untyped_storage().data_ptr():
+            return None
+        return int(v.storage_offset()) - int(self.buffers[0].storage_offset())
+
+    def slot_of(self, vecs):
+        return self._owner.get(self._key(vecs))
+
+    def release(self, vecs):
+        """give the slot(s) of a block back (blocks that do not live in the pool are ignored)"""
+        got = self._owner.pop(self._key(vecs), None)
+        if got is not None:
+            for j in range(got[0], got[0] + got[1]):
+                self._used[j] = False
+
+
 class RowMover:
     """Moves the rows of local [rows, nb] matrices between the row layouts of a sharded plan.  Host logic only
     (index maps from `tcc_shard_layout`); the tensors may live on the GPU (NCCL) or on the CPU (gloo tests)."""
@@ -221,9 +351,13 @@ class RowMover:
         # rows[l][r]: storage rows of rank r in layout l, ascending (= its local row order)
         self.rows = [[np.nonzero(own == r)[0] for r in range(self.world)] for own in self.owner]
         self._moves = {}
+        self._push = {}
         self._rows_dev = {}
         self.reshards = 0
         self.timer = PhaseTimer(torch, False)
+        self.pool = None  # ShardPool, attached by the driver
+        self.lib = plan.lib
+        self.max_rows = max(len(r) for lay in self.rows for r in lay)
 
     def rows_dev(self, layout: int, rank: int):
         """Storage rows of `rank` in `layout` as an index tensor on the device (cached)."""
@@ -259,28 +393,83 @@ class RowMover:
             self._moves[key] = (rounds, len(mine_to))
         return self._moves[key]
 
-    def reshard(self, vecs: List["torch.Tensor"], l_from: int, l_to: int) -> List["torch.Tensor"]:
-        """vecs[i]: local [rows, nb] matrix of the i-th local rank in layout l_from -> the same in layout l_to."""
+    def _push_plan(self, l_from: int, l_to: int, rank: int):
+        """index arrays of the peer-memory move of `rank`: for every row it holds in l_from, the local source row, the
+        owner in l_to and the row's position among that owner's rows"""
+        key = (l_from, l_to, rank)
+        if key not in self._push:
+            t = self.torch
+            mine = self.rows[l_from][rank]
+            dst_rank = self.owner[l_to][mine].astype(np.int32)
+            dst_row = np.empty(len(mine), dtype=np.int64)
+            for q in range(self.world):
+                sel = dst_rank == q
+                if sel.any():
+                    dst_row[sel] = np.searchsorted(self.rows[l_to][q], mine[sel])
+            self._push[key] = (t.arange(len(mine), dtype=t.int64, device=self.device),
+                               t.as_tensor(dst_row, dtype=t.int64, device=self.device),
+                               t.as_tensor(dst_rank, dtype=t.int32, device=self.device))
+        return self._push[key]
+
+    def _stream(self):
+        import ctypes as C
+
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def reshard(self, vecs: List["torch.Tensor"], l_from: int, l_to: int, keep_src: bool = False) -> List["torch.Tensor"]:
+        """vecs[i]: local [rows, ...] block of the i-th local rank in layout l_from -> the same in layout l_to, in a
+        fresh slot of the pool; the source slot is released unless keep_src.  With a peer-mapped pool every row is
+        written straight into the destination slot of its new owner (tcc_push_rows, one pass over NVLink) between two
+        stream barriers: the first makes sure every rank has finished with whatever lived in the destination slot, the
+        second that all rows have arrived.  Otherwise: pack, NCCL all-to-all, unpack in rounds of chunk_bytes."""
+        import ctypes as C
+
+        from . import _lib
+
         t = self.torch
         if l_from == l_to:
             return vecs
         self.reshards += 1
-        row_elems = int(vecs[0][0].numel()) if vecs[0].shape[0] else int(np.prod(vecs[0].shape[1:]))
-        plans = [self._move_plan(l_from, l_to, r, row_elems) for r in self.comm.local_ranks]
-        out = [t.empty((mp[1],) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device) for v, mp in zip(vecs, plans)]
-        for j in range(len(plans[0][0])):
-            rnd = [mp[0][j] for mp in plans]
-            # pack the rows by destination (one gather), one all-to-all, unpack by local row (one scatter)
-            with self.timer.phase("move_pack"):
-                send = [v.index_select(0, r_[0]) for v, r_ in zip(vecs, rnd)]
-            with self.timer.phase("move_all_to_all", sum(int(x.numel()) * 8 for x in send)):
-                recv = self.comm.exchange_packed(send, [r_[2] for r_ in rnd], [r_[3] for r_ in rnd])
-            del send
-            with self.timer.phase("move_unpack"):
-                for new, r_, got in zip(out, rnd, recv):
-                    if r_[1].numel():
-                        new.index_copy_(0, r_[1], got)
-            del recv
+        trailing = tuple(vecs[0].shape[1:])
+        row_elems = int(np.prod(trailing))
+        new_rows = [len(self.rows[l_to][r]) for r in self.comm.local_ranks]
+        pool = self.pool
+        if pool is None:  # CPU tests of the transport: plain tensors
+            out = [t.empty((n,) + trailing, dtype=vecs[0].dtype, device=self.device) for n in new_rows]
+        else:
+            out = pool.empty(new_rows, trailing)
+        if pool is not None and pool.p2p:
+            first, _ = pool.slot_of(out)
+            nbytes = sum(int(v.numel()) * 8 for v in vecs)
+            with self.timer.phase("move_barrier"):
+                self.comm.stream_barrier()
+            with self.timer.phase("move_push", nbytes):
+                for k, r in enumerate(self.comm.local_ranks):
+                    src_row, dst_row, dst_rank = self._push_plan(l_from, l_to, r)
+                    if vecs[k].shape[0]:
+                        _lib.check(self.lib.tcc_push_rows(
+                            int(self.device.index), C.c_void_p(vecs[k].data_ptr()), row_elems, int(vecs[k].shape[0]),
+                            C.c_void_p(src_row.data_ptr()), C.c_void_p(dst_row.data_ptr()), C.c_void_p(dst_rank.data_ptr()),
+                            C.c_void_p(pool.peer_ptrs[k].data_ptr()), first * pool.slot, self._stream()))
+            with self.timer.phase("move_barrier"):
+                self.comm.stream_barrier()
+        else:
+            plans = [self._move_plan(l_from, l_to, r, row_elems) for r in self.comm.local_ranks]
+            for j in range(len(plans[0][0])):
+                rnd = [mp[0][j] for mp in plans]
+                # pack the rows by destination (one gather), one all-to-all, unpack by local row (one scatter)
+                with self.timer.phase("move_pack"):
+                    send = [v.index_select(0, r_[0]) for v, r_ in zip(vecs, rnd)]
+                with self.timer.phase("move_all_to_all", sum(int(x.numel()) * 8 for x in send)):
+                    recv = self.comm.exchange_packed(send, [r_[2] for r_ in rnd], [r_[3] for r_ in rnd])
+                del send
+                with self.timer.phase("move_unpack"):
+                    for new, r_, got in zip(out, rnd, recv):
+                        if r_[1].numel():
+                            new.index_copy_(0, r_[1], got)
+                del recv
+        if pool is not None and not keep_src:
+            pool.release(vecs)
         return out
 
     # ---- row-sharded [rows, nb]  <->  column-sharded [na, cols] (all rows, a block of columns) ----------------
@@ -383,6 +572,16 @@ class ShardedUCC:
         self.mover = RowMover(p0, comm, self.device, chunk_bytes)
         self.rows = self.mover.rows
         self.timer = self.mover.timer  # one PhaseTimer for the driver and its row mover (off unless enabled)
+        # every shard-sized block lives in a fixed pool of slots (ShardPool): 4 cover the deepest point of the path (ket,
+        # sigma, the moved copy of a sigma pass and its partial result); the fused reverse sweep moves (ket, bra) as one
+        # double-size block and gets 6 so that two free neighbouring slots always exist
+        slot = max(self.mover.max_rows, 1) * self.nb
+        total = torch.cuda.get_device_properties(self.device).total_memory
+        if fuse_reverse_moves == "auto":
+            fuse_reverse_moves = self.world > 1 and 2 * 8 * slot < total // 8
+        self.fuse_reverse_moves = bool(fuse_reverse_moves)
+        self.pool = ShardPool(comm, self.device, slot, 6 if self.fuse_reverse_moves else 4)
+        self.mover.pool = self.pool
         self.ref2int = p0.storage_order()  # storage address of every per-spin string, by reference address
         self.hf_row = int(self.ref2int[0])  # HF determinant = reference address 0 of both spins
 
@@ -394,8 +593,11 @@ class ShardedUCC:
         for st in self.states:
             st.plan.set_hamiltonian(int1e, int2e)
 
-    def _reshard(self, vecs, l_from, l_to):
-        return self.mover.reshard(vecs, l_from, l_to)
+    def _reshard(self, vecs, l_from, l_to, keep_src=False):
+        return self.mover.reshard(vecs, l_from, l_to, keep_src)
+
+    def _rows_of(self, layout):
+        return [len(self.rows[layout][st.rank]) for st in self.states]
 
     # ---- the path -----------------------------------------------------------------------------------
     def _forward(self, params, init_sparse=None):
@@ -410,19 +612,17 @@ class ShardedUCC:
             ia = self.ref2int[np.asarray(init_sparse[0], dtype=np.int64)].astype(np.int64)
             ib = self.ref2int[np.asarray(init_sparse[1], dtype=np.int64)].astype(np.int64)
             iv = np.asarray(init_sparse[2], dtype=np.float64)
-        kets = []
-        for st in self.states:
+        self.pool.reset()  # a new evaluation owns the whole pool
+        kets = self.pool.zeros(self._rows_of(first), (self.nb,))
+        for ket, st in zip(kets, self.states):
             st.plan.shard_set_params(params)
             rows = self.rows[first][st.rank]
-            ket = t.zeros((len(rows), self.nb), dtype=t.float64, device=self.device)
             pos = np.searchsorted(rows, ia)
             pos[pos >= len(rows)] = 0
             mine = (rows[pos] == ia) if len(rows) else np.zeros(len(ia), dtype=bool)
             if mine.any():
                 flat = t.as_tensor(pos[mine] * self.nb + ib[mine], dtype=t.int64, device=self.device)
                 ket.view(-1).index_put_((flat,), t.as_tensor(iv[mine], dtype=t.float64, device=self.device))
-            kets.append(ket)
-            del ket
         layout = first
         for seg, (l, _, _) in enumerate(self.segments):
             kets = self._reshard(kets, layout, l)
@@ -457,14 +657,11 @@ class ShardedUCC:
         the same layout.  Needs no full vector on any rank."""
         t = self.torch
         l3 = self.states[0].plan.shard_sigma_layouts()
-        sig = []
-        for st, ket in zip(self.states, kets):
-            with self.timer.phase("sigma_kernels"):
-                s_loc = t.zeros_like(ket)
+        with self.timer.phase("sigma_kernels"):
+            sig = self.pool.zeros(self._rows_of(layout), (self.nb,))
+            for st, ket, s_loc in zip(self.states, kets, sig):
                 if ket.numel():
                     st.plan.shard_sigma_bb(ket, s_loc)
-            sig.append(s_loc)
-            del s_loc
         # alpha-beta: pass i in layout l3[i].  The passes live in helper methods: a tensor that a loop variable of this
         # frame still names would stay allocated through the next pass (a fifth shard at (20e,20o) is an OOM).
         for i, l in enumerate(l3):
@@ -505,22 +702,21 @@ class ShardedUCC:
         return [mine[k][: len(self.rows[layout][st.rank])] for k, st in enumerate(self.states)]
 
     def _sigma_ab_pass(self, i, l, kets, layout, sig):
-        """sig += pass i of the opposite-spin terms.  Peak: kets + sig + the moved copy + its partial sigma."""
-        t = self.torch
-        c_i = self._reshard(kets, layout, l)
-        part = []
-        for k in range(len(self.states)):
-            with self.timer.phase("sigma_kernels"):
-                s_i = t.zeros_like(c_i[k])
-                if s_i.numel():
-                    self.states[k].plan.shard_sigma_ab(i, c_i[k], s_i)
-            part.append(s_i)
-            del s_i
+        """sig += pass i of the opposite-spin terms.  Peak: kets + sig + the moved copy + its partial sigma = 4 slots."""
+        c_i = self._reshard(kets, layout, l, keep_src=True)
+        with self.timer.phase("sigma_kernels"):
+            part = self.pool.zeros(self._rows_of(l), (self.nb,))
+            for k in range(len(self.states)):
+                if part[k].numel():
+                    self.states[k].plan.shard_sigma_ab(i, c_i[k], part[k])
+        if c_i is not kets:
+            self.pool.release(c_i)
         del c_i
         part = self._reshard(part, l, layout)
         with self.timer.phase("sigma_accumulate"):
             for k in range(len(sig)):
                 sig[k] += part[k]
+        self.pool.release(part)
 
     def _sigma_aa_piece(self, j, pieces, kets, layout, sig):
         t = self.torch
@@ -573,16 +769,22 @@ class ShardedUCC:
             energy = float(parts[0][0])
         if not want_grad:
             return energy, None
-        fuse = self.fuse_reverse_moves
-        if fuse == "auto":
-            total = t.cuda.get_device_properties(self.device).total_memory
-            fuse = self.world > 1 and 2 * 8 * max(k_.numel() for k_ in kets) < total // 8
-        if fuse:
-            # element-interleaved block [rows, nb, 2] when every batch has lean streams (16-byte elements in the kernel
-            # too), else row-interleaved [rows, 2, nb] (two vectors with a row stride)
+        if self.fuse_reverse_moves:
+            # (ket, bra) as ONE block: a segment boundary costs one row move instead of two.  Element-interleaved
+            # [rows, nb, 2] when every batch has lean streams (16-byte elements in the kernel too), else row-interleaved
+            # [rows, 2, nb] (two vectors with a row stride)
             il = all(st.plan.shard_can_interleave() for st in self.states)
             with self.timer.phase("reverse_interleave"):
-                both = [t.stack((kets[k], bras[k]), dim=2 if il else 1) for k in range(len(kets))]
+                both = self.pool.empty(self._rows_of(layout), (self.nb, 2) if il else (2, self.nb))
+                for k in range(len(both)):
+                    if il:
+                        both[k][:, :, 0] = kets[k]
+                        both[k][:, :, 1] = bras[k]
+                    else:
+                        both[k][:, 0] = kets[k]
+                        both[k][:, 1] = bras[k]
+            self.pool.release(kets)
+            self.pool.release(bras)
             del kets, bras
             for seg in range(len(self.segments) - 1, -1, -1):
                 l = self.segments[seg][0]
@@ -603,7 +805,7 @@ class ShardedUCC:
                 bras = self._reshard(bras, layout, l)
                 layout = l
                 with self.timer.phase("reverse_kernels"):
-                    for k, st in enumerate(self.states):  # by index: no loop variable keeps a shard of the old layout alive
+                    for k, st in enumerate(self.states):
                         if kets[k].numel():
                             st.plan.shard_reverse(seg, kets[k], bras[k])
         with self.timer.phase("gradient_allreduce"):

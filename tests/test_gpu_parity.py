@@ -675,8 +675,9 @@ def test_sharded_full_size_16o_matches_single_gpu():
 
 
 def test_sharded_distributed_sigma_peak_memory():
-    """The distributed H c must peak at ket + sigma + one moved copy + its partial (4 shards per rank, plus bounded
-    staging): a fifth live shard is an out-of-memory error at (20e,20o) on 8 GPUs (35.9 GB shards, 180 GB HBM)."""
+    """Every shard-sized block of the sharded driver lives in a fixed pool of FOUR slots per rank (ket + sigma + one moved
+    copy + its partial); a fifth live shard is an out-of-memory error at (20e,20o) on 8 GPUs (33.5 GiB shards, 180 GB
+    HBM).  The distributed H c must run inside the pool (exhaustion raises) and allocate next to nothing beyond it."""
     import torch
 
     from tencirchem_b200.sharded import LocalComm, ShardedUCC
@@ -685,20 +686,32 @@ def test_sharded_distributed_sigma_peak_memory():
     int1e, int2e = random_integral(n)
     ucc = UCCSD.from_integral(int1e, int2e, n)
     ex_ops, param_ids = ucc.ex_ops[:40], list(range(40))
-    eng = ShardedUCC(2 * n, n, ex_ops, param_ids, LocalComm(world), sigma_mode="distributed", chunk_bytes=256 << 10)
+    eng = ShardedUCC(2 * n, n, ex_ops, param_ids, LocalComm(world), sigma_mode="distributed", chunk_bytes=256 << 10,
+                     fuse_reverse_moves=False)
+    assert eng.pool.n_slots == 4
     eng.set_hamiltonian(int1e, int2e)
     params = 0.1 * _params(40)
     kets, layout = eng._forward(params)
-    shard = max(k.numel() for k in kets) * 8
+    shard = eng.pool.slot * 8
     torch.cuda.synchronize()
     base = torch.cuda.memory_allocated()
     torch.cuda.reset_peak_memory_stats()
     bras = eng._sigma_distributed(kets, layout)
     torch.cuda.synchronize()
-    extra = torch.cuda.max_memory_allocated() - base  # beyond the kets, for both virtual ranks
-    assert extra < world * 3.4 * shard, (extra / shard, "shards beyond the kets")
+    extra = torch.cuda.max_memory_allocated() - base  # outside the pool: the staging of the column transposes only
+    assert extra < world * 0.5 * shard, (extra / shard, "shards allocated outside the pool")
+    assert sum(eng.pool._used) == 2  # ket and sigma; every temporary slot was given back
     # and the result is H c: compare with the replicated mode
     eng2 = ShardedUCC(2 * n, n, ex_ops, param_ids, LocalComm(world), sigma_mode="replicated")
     eng2.set_hamiltonian(int1e, int2e)
     e1 = sum(float(torch.dot(b.reshape(-1), k.reshape(-1))) for b, k in zip(bras, kets))
     assert abs(e1 - eng2.energy(params)) < E_TOL
+    # the whole evaluation, gradient included, runs in the four slots, and equally through the pack / exchange / unpack
+    # transport of a system without peer mapping
+    e_p2p, g_p2p = eng.energy_and_grad(params)
+    eng3 = ShardedUCC(2 * n, n, ex_ops, param_ids, LocalComm(world, peer_memory=False), sigma_mode="distributed",
+                      chunk_bytes=256 << 10, fuse_reverse_moves=True)
+    assert eng3.pool.n_slots == 6 and not eng3.pool.p2p and eng.pool.p2p
+    eng3.set_hamiltonian(int1e, int2e)
+    e_st, g_st = eng3.energy_and_grad(params)
+    assert abs(e_p2p - e_st) < E_TOL and np.abs(g_p2p - g_st).max() < G_TOL

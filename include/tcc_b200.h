@@ -141,12 +141,28 @@ int64_t tcc_op_support_bytes(const tcc_plan* plan, int j);
 /* kernel launches issued by this plan since creation (for bench.py's gpu_launches) */
 int64_t tcc_launch_count(const tcc_plan* plan);
 
+/* ---- operator-pool gradients (ADAPT-VQE screening) ----------------------------------------
+ * docs/source/tutorial_jupyter/adapt_vqe.ipynb cell 9 loops over the pool calling apply_excitation and a dot product
+ * per operator.  Here the excitation list of `plan` IS the pool: out_host[k] = <sigma| G_k |c> for every excitation k
+ * of the plan in one batched launch set (the reverse-sweep kernels at zero angles).  c_dev / sigma_dev: reference-order
+ * CI vectors on the device (sigma = H c from tcc_apply_h), left unchanged.  The ADAPT gradient of a pool entry is twice
+ * the sum over its excitations. */
+int tcc_pool_gradients(tcc_plan* plan, const double* c_dev, const double* sigma_dev, double* out_host /* [num_ops] */,
+                       void* stream);
+
 /* ---- reduced density matrices (the immediate consumer of the CI vector) ------------------
  * Replaces UCC.make_rdm1 / make_rdm2 in the MO basis (ucc.py:755-852), which copy the CI vector to the host and call
  * pyscf direct_spin1.make_rdm1 / make_rdm12.  c_dev: reference-order CI vector on the device.  Spin-traced:
  * rdm1[p,q] = <q+ p> ([n, n]); rdm2[p,q,r,s] = <p+ r+ s q> ([n, n, n, n], chemists' order, so that
  * E = sum h1[p,q] rdm1[p,q] + 1/2 sum (pq|rs) rdm2[p,q,r,s]).  Either output may be NULL.  Not for hcb plans. */
 int tcc_make_rdm12(tcc_plan* plan, const double* c_dev, double* rdm1_host, double* rdm2_host, void* stream);
+
+/* pUCCD density-matrix elements on the hard-core-boson CI vector.  Replaces the numpy mask loops of
+ * PUCCD.make_rdm1 / make_rdm2 (tencirchem/static/puccd.py:148-203).  c_dev: the hcb CI vector in reference order on
+ * the device.  occ[p] = <n_p> (one spin), hop[p,q] = sum_I c_I c_{I with the pair moved q -> p} (symmetric, zero
+ * diagonal), both[p,q] = <n_p n_q> (symmetric, both[p,p] = occ[p]); all [n] / [n, n] host arrays.  hcb plans only. */
+int tcc_make_rdm12_hcb(tcc_plan* plan, const double* c_dev, double* occ_host, double* hop_host, double* both_host,
+                       void* stream);
 
 /* ---- multi-GPU: alpha-row sharded plans -----------------------------
  * The [na, nb] CI matrix is split by alpha rows over `world` ranks (one process per GPU, world a power of

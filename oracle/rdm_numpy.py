@@ -44,3 +44,35 @@ def make_rdm12(civector, norb, nelec):
 
 def make_rdm1(civector, norb, nelec):
     return make_rdm12(civector, norb, nelec)[0]
+
+
+def make_rdm12_hcb(civector, norb, nelec):
+    """pUCCD RDMs on the hard-core-boson CI vector, restating tencirchem/static/puccd.py:148-203 (MO basis, before
+    embed_rdm_cas / rdm_mo2ao): the mask loops over the pair-occupation strings, the partner address through the
+    string -> address map (cistring.strs2addr upstream)."""
+    strings = np.asarray(make_strings(norb, nelec // 2), dtype=np.int64)
+    addr = {int(s): i for i, s in enumerate(strings)}
+    c = np.asarray(civector, dtype=np.float64)
+    rdm1 = np.zeros((norb, norb))
+    for i in range(norb):
+        m = 1 << i
+        rdm1[i, i] = 2 * float(c @ (((strings & m) == m) * c))
+    rdm2 = np.zeros((norb,) * 4)
+    for p in range(norb):
+        for q in range(p + 1):
+            mq, mp = 1 << q, 1 << p
+            mask = (strings & mq) == mq
+            if p == q:
+                value = float(c @ (mask * c))
+            else:
+                mask = mask & (((~strings) & mp) == mp)
+                partner = np.array([addr.get(int(s), 0) for s in strings ^ (mp | mq)])
+                value = float(c @ (mask * c[partner]))
+            rdm2[p, q, p, q] = rdm2[q, p, q, p] = value
+            if p == q:
+                continue
+            both = (strings & (mp | mq)) == (mp | mq)
+            value = float(c @ (both * c))
+            rdm2[p, p, q, q] = rdm2[q, q, p, p] = 2 * value
+            rdm2[p, q, q, p] = rdm2[q, p, p, q] = -value
+    return rdm1, 2 * rdm2

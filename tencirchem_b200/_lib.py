@@ -59,6 +59,7 @@ SIGNATURES = {
     "tcc_op_support_bytes": (C.c_int64, [_p, C.c_int]),
     "tcc_launch_count": (C.c_int64, [_p]),
     "tcc_make_rdm12": (C.c_int, [_p, _p, _dp, _dp, _p]),
+    "tcc_make_rdm12_hcb": (C.c_int, [_p, _p, _dp, _dp, _dp, _p]),
     "tcc_plan_create_sharded": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
     "tcc_shard_info": (C.c_int, [_p, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
     "tcc_shard_segment": (C.c_int, [_p, C.c_int, _ip, _ip, _ip]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "tcc_shard_reverse_strided": (C.c_int, [_p, C.c_int, _p, _p, C.c_int64, _p]),
     "tcc_shard_reverse_interleaved": (C.c_int, [_p, C.c_int, _p, _p]),
     "tcc_shard_can_interleave": (C.c_int, [_p]),
+    "tcc_pool_gradients": (C.c_int, [_p, _p, _p, _dp, _p]),
     "tcc_push_rows": (C.c_int, [C.c_int, _p, C.c_int64, C.c_int64, _p, _p, _p, _p, C.c_int64, _p]),
     "tcc_shard_gradient": (C.c_int, [_p, _dp, _p]),
     "tcc_apply_h_rows": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, _p]),

@@ -236,6 +236,38 @@ class UCC:
         self._check_engine(engine)
         return engine_ucc.apply_excitation(state, self.n_qubits, self.n_elec, ex_op, hcb=self.hcb)
 
+    def pool_gradients(self, pool: Sequence[Sequence[Tuple[int, ...]]], params=None, engine: str = None) -> np.ndarray:
+        """ADAPT-VQE screening (adapt_vqe.ipynb cell 9): for every entry of `pool` (a list of excitation tuples that
+        share one parameter) the energy gradient 2 * sum_op <H psi| G_op |psi> at the current state psi = civector(params)
+        -- one batched launch set for the WHOLE pool (tcc_pool_gradients) instead of one apply_excitation + dot product
+        per operator.  psi and H psi never leave the GPU."""
+        import torch
+
+        from .evolve_civector import _bind_hamiltonian, get_plan
+
+        self._sanity_check()
+        self._check_engine(engine)
+        flat = [tuple(int(i) for i in op) for entry in pool for op in entry]
+        owner = [k for k, entry in enumerate(pool) for _ in entry]
+        if not flat:
+            return np.zeros(len(pool))
+        params = self._check_params_argument(params)
+        state_plan = get_plan(self.n_qubits, self.n_elec, self.ex_ops, self.param_ids, self.hcb)
+        _bind_hamiltonian(state_plan, self.hamiltonian)
+        psi = torch.empty(state_plan.size, dtype=torch.float64, device=f"cuda:{state_plan.device}")
+        init = None
+        if self.init_state is not None:
+            init = torch.as_tensor(engine_ucc.translate_init_state(self.init_state, self.n_qubits, lambda: get_ci_strings(self.n_qubits, self.n_elec, self.hcb)),
+                                   dtype=torch.float64, device=psi.device)
+        state_plan.civector_dev(params, psi, init)
+        hpsi = torch.empty_like(psi)
+        state_plan.apply_h_dev(psi, hpsi)
+        pool_plan = get_plan(self.n_qubits, self.n_elec, tuple(flat), tuple(range(len(flat))), self.hcb)
+        per_op = pool_plan.pool_gradients_dev(psi, hpsi)
+        out = np.zeros(len(pool))
+        np.add.at(out, owner, 2.0 * per_op)
+        return out
+
     # ---- reduced density matrices (ucc.py:755-852), MO basis of the integrals the ansatz was built from ----
     def _rdm12(self, statevector=None):
         import torch
@@ -477,3 +509,46 @@ class PUCCD(UCC):
         """puccd.py:101-146."""
         ops = [(self.no + a, i) for i in range(self.no) for a in range(self.nv - 1, -1, -1)]
         return ops, list(range(len(ops))), [0.0] * len(ops)
+
+    # ---- reduced density matrices on the hard-core-boson vector (puccd.py:148-203), MO basis ----
+    def _rdm_hcb(self, statevector=None):
+        import torch
+
+        from .evolve_civector import default_device, get_plan
+
+        civector = self.civector() if statevector is None else np.asarray(statevector, dtype=np.float64)
+        if len(civector) == self.statevector_size and self.statevector_size != self.civector_size:
+            civector = civector[self.get_ci_strings()]  # ucc.py:743-745
+        if len(civector) != self.civector_size:
+            raise ValueError(f"Incompatible statevector size: {len(civector)}")
+        plan = get_plan(self.n_qubits, self.n_elec, self.ex_ops or (), self.param_ids or (), self.hcb)
+        c_dev = torch.as_tensor(np.ascontiguousarray(civector), dtype=torch.float64, device=torch.device("cuda", default_device()))
+        return plan.make_rdm12_hcb_dev(c_dev)
+
+    def make_rdm1(self, statevector=None, basis: str = "MO") -> np.ndarray:
+        """puccd.py:148-165: diagonal, rdm1[i, i] = 2 <n_i>; the occupations are reduced on the GPU."""
+        if basis != "MO":
+            raise ValueError("this build works from MO integrals: only basis='MO' is available")
+        occ, _, _ = self._rdm_hcb(statevector)
+        return np.diag(2.0 * occ)
+
+    def make_rdm2(self, statevector=None, basis: str = "MO") -> np.ndarray:
+        """puccd.py:167-203: the pair-hop and pair-pair elements come from one GPU reduction per (p, q); the
+        assembly into [n, n, n, n] (with the reference's final factor 2) is index bookkeeping on the host."""
+        if basis != "MO":
+            raise ValueError("this build works from MO integrals: only basis='MO' is available")
+        occ, hop, both = self._rdm_hcb(statevector)
+        n = self.n_qubits
+        rdm2 = np.zeros((n, n, n, n))
+        for p in range(n):
+            rdm2[p, p, p, p] = occ[p]
+            for q in range(p):
+                rdm2[p, q, p, q] = rdm2[q, p, q, p] = hop[p, q]
+                rdm2[p, p, q, q] = rdm2[q, q, p, p] = 2 * both[p, q]
+                rdm2[p, q, q, p] = rdm2[q, p, p, q] = -both[p, q]
+        return 2.0 * rdm2
+
+    @property
+    def e_puccd(self) -> float:
+        """puccd.py:231-236."""
+        return self.energy()

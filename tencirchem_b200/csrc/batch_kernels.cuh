@@ -48,7 +48,10 @@ struct SetStrides {
 struct TileRect {
     int pa_lo, pa_cnt, pb_lo, pb_cnt;
     size_t smem_fwd, smem_rev;
-    size_t smem_il;  // reverse sweep on interleaved (ket, bra) elements
+    size_t smem_il;   // reverse sweep on interleaved (ket, bra) elements (lean_batch_kernel<3>)
+    size_t smem_il2;  // the same for rev_il_kernel
+    int tile_bytes_il2;
+    int max_rows;
 };
 
 // Auxiliary streams for the rectangle launches of one batch: the rectangles are independent sets of tiles, so they
@@ -64,8 +67,10 @@ struct StreamFan {
 cudaError_t batch_kernels_configure();
 size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv);
 size_t lean_smem_bytes(int max_rows, int max_cols, int nops, int nv);
+size_t rev_il_smem_bytes(int max_rows, int max_cols, int nops, int* tile_bytes_max);
 void launch_batch_reverse_il(double* kb, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan);
+                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan,
+                             int mode, int persist_ctas);
 void launch_interleave(const double* a, const double* b, double* out, int64_t n, cudaStream_t st);
 void launch_deinterleave(const double* in, double* a, double* b, int64_t n, cudaStream_t st);
 void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,

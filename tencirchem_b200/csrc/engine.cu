@@ -145,6 +145,8 @@ struct tcc_plan {
     int lean = 1;           // lean per-thread streams for two-sided batches (TCC_B200_LEAN=0: the plain pair lists)
     int lean_fwd = 0;       // forward sweep on the lean kernel too (TCC_B200_LEAN_FWD=1); measured slower than batch_kernel<1>
     int rev_interleave = 1; // reverse sweep on interleaved (ket, bra) elements (TCC_B200_REV_IL=0: two vectors)
+    int rev_il_mode = 2;    // 0: lean_batch_kernel<3>; 1: rev_il_kernel, one tile per CTA; 2: rev_il_kernel, persistent
+    int persist_ctas = 296; // CTAs of the persistent launch (2 per SM)
     double* io1 = nullptr;  // reference-order staging for the host-buffer entry points
     double* io2 = nullptr;
     double* partials = nullptr;
@@ -312,6 +314,9 @@ static int upload_batches(tcc_plan* p) {
                     r.smem_fwd = db.fwd.lean ? lean_smem_bytes(xa[2], cols, db.nops, 1) : batch_smem_bytes(xa[2], cols, db.nops, 1);
                     r.smem_rev = db.rev.lean ? lean_smem_bytes(xa[2], cols, db.nops, 2) : batch_smem_bytes(xa[2], cols, db.nops, 2);
                     r.smem_il = db.rev.lean ? lean_smem_bytes(xa[2], cols, db.nops, 3) : 0;
+                    r.max_rows = xa[2];
+                    r.tile_bytes_il2 = 0;
+                    r.smem_il2 = db.rev.lean ? rev_il_smem_bytes(xa[2], cols, db.nops, &r.tile_bytes_il2) : 0;
                     db.smem_fwd = std::max(db.smem_fwd, r.smem_fwd);
                     db.smem_rev = std::max(db.smem_rev, r.smem_rev);
                     if (r.pa_cnt > 0 && r.pb_cnt > 0) out->push_back(r);
@@ -319,7 +324,7 @@ static int upload_batches(tcc_plan* p) {
         };
         make_rects(split >= 2, &db.rects);
         make_rects(split >= 1, &db.rects_rev);
-        for (const TileRect& r : db.rects_rev) db.smem_rev = std::max(db.smem_rev, r.smem_il);
+        for (const TileRect& r : db.rects_rev) db.smem_rev = std::max(db.smem_rev, std::max(r.smem_il, r.smem_il2));
         if (db.smem_rev > 232448)
             return fail(TCC_ERR_BAD_ARGUMENT, "batch tile does not fit in shared memory: lower TCC_B200_TILE_ELEMS");
         max_part = std::max(max_part, size_t(db.nops) * size_t(db.n_tiles));
@@ -439,6 +444,7 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
               p->batch_threads >= 64;
     p->rev_interleave = p->lean && env_int("TCC_B200_REV_IL", 1) != 0;
     p->lean_fwd = p->lean && env_int("TCC_B200_LEAN_FWD", 0) != 0;
+    p->rev_il_mode = env_int("TCC_B200_REV_IL_MODE", 2);
     p->hp.error.clear();
     p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0, rank, world, p->lean ? p->batch_threads : 0);
     if (!p->hp.error.empty()) {
@@ -472,6 +478,11 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
         return code;
     };
     if (int rc_dev = use_device(p)) return bail(rc_dev);
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        p->persist_ctas = env_int("TCC_B200_PERSIST_CTAS", 2 * sms);
+    }
     for (size_t h = 0; h < p->hp.hops.size(); ++h)
         if (upload_hop(p, int(h))) return bail(TCC_ERR_CUDA);
     if (int rc2 = upload_batches(p)) return bail(rc2);
@@ -611,6 +622,23 @@ int tcc_excitation_tables(const tcc_plan* p, int j, uint64_t* perm_host, int8_t*
     return 0;
 }
 
+// strings, binomials and the storage bit positions of an hcb plan on the device (sigma_hcb_kernel, hcb_rdm_kernel)
+static int ensure_hcb_tables(tcc_plan* p) {
+    if (p->d_strings) return 0;
+    HostPlan& hp = p->hp;
+    const int n = hp.n;
+    std::vector<int64_t> bin(size_t(n + 2) * (n + 2));
+    for (int i = 0; i < n + 2; ++i)
+        for (int j = 0; j < n + 2; ++j) bin[size_t(i) * (n + 2) + j] = hp.binom[i][j];
+    CUDA_TRY(dev_alloc(p, &p->d_strings, size_t(hp.nstr)));
+    CUDA_TRY(dev_alloc(p, &p->d_binom, bin.size()));
+    CUDA_TRY(dev_alloc(p, &p->d_bitpos, size_t(32)));
+    CUDA_TRY(cudaMemcpy(p->d_bitpos, hp.bitpos.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p->d_strings, hp.strings.data(), hp.nstr * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p->d_binom, bin.data(), bin.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 int tcc_set_hamiltonian(tcc_plan* p, const double* int1e, const double* int2e) {
     if (!p || !int1e || !int2e) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     if (int rc_dev = use_device(p)) return rc_dev;
@@ -626,23 +654,15 @@ int tcc_set_hamiltonian(tcc_plan* p, const double* int1e, const double* int2e) {
                 d2[q * n + r] = 4 * i2(q, q, r, r) - 2 * i2(q, r, q, r);
             }
         }
-        std::vector<int64_t> bin(size_t(n + 2) * (n + 2));
-        for (int i = 0; i < n + 2; ++i)
-            for (int j = 0; j < n + 2; ++j) bin[size_t(i) * (n + 2) + j] = hp.binom[i][j];
-        if (!p->d_strings) {
-            CUDA_TRY(dev_alloc(p, &p->d_strings, size_t(hp.nstr)));
+        if (int rc = ensure_hcb_tables(p)) return rc;
+        if (!p->d_diag1) {
             CUDA_TRY(dev_alloc(p, &p->d_diag1, size_t(n)));
             CUDA_TRY(dev_alloc(p, &p->d_hop, size_t(n) * n));
             CUDA_TRY(dev_alloc(p, &p->d_diag2, size_t(n) * n));
-            CUDA_TRY(dev_alloc(p, &p->d_binom, bin.size()));
-            CUDA_TRY(dev_alloc(p, &p->d_bitpos, size_t(32)));
         }
-        CUDA_TRY(cudaMemcpy(p->d_bitpos, hp.bitpos.data(), n * sizeof(int), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(p->d_strings, hp.strings.data(), hp.nstr * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(p->d_diag1, d1.data(), n * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(p->d_hop, hop.data(), hop.size() * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(p->d_diag2, d2.data(), d2.size() * sizeof(double), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(p->d_binom, bin.data(), bin.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
         p->has_h = true;
         return 0;
     }
@@ -864,7 +884,7 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
                     in_kb = true;
                 }
                 launch_batch_reverse_il(p->kb, hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
-                                        SetStrides{0, 0, 0, 0}, st, &p->fan);
+                                        SetStrides{0, 0, 0, 0}, st, &p->fan, p->rev_il_mode, p->persist_ctas);
             } else {
                 if (in_kb) {
                     launch_deinterleave(p->kb, ket, bra, hp.N, st);
@@ -1008,6 +1028,35 @@ int tcc_energy_and_grad(tcc_plan* p, const double* params_host, const double* in
     if (int rc_dev = use_device(p)) return rc_dev;
     if (int rc_sh = whole_vector_only(p)) return rc_sh;
     return energy_impl(p, params_host, init_dev, energy_host, grad_host, cudaStream_t(stream));
+}
+
+// ADAPT-VQE pool screening (docs/source/tutorial_jupyter/adapt_vqe.ipynb cell 9: for every pool operator
+// 2 * bra . apply_excitation(ket, op) with bra = H ket): the excitation list of THIS plan is the operator pool, and
+// <sigma| G_k |c> for all k is the reverse sweep with every angle zero -- the rotations are exact identities, so one
+// batched launch set over (c, sigma) yields all pool gradients; nothing is applied in sequence and the order is
+// irrelevant.  c_dev, sigma_dev: reference-order CI vectors on the device (not modified); out_host[k] = <sigma|G_k|c>.
+int tcc_pool_gradients(tcc_plan* p, const double* c_dev, const double* sigma_dev, double* out_host, void* stream) {
+    if (!p || !c_dev || !sigma_dev || !out_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    if (int rc_sh = whole_vector_only(p)) return rc_sh;
+    HostPlan& hp = p->hp;
+    const int m = int(hp.ops.size());
+    if (m == 0) return 0;
+    cudaStream_t st = cudaStream_t(stream);
+    if (int rc = ensure_vec(p, &p->ket)) return rc;
+    if (int rc = ensure_vec(p, &p->bra)) return rc;
+    to_storage(p, c_dev, p->ket, st);
+    to_storage(p, sigma_dev, p->bra, st);
+    std::vector<double> zeros(size_t(std::max(hp.n_params, 1)), 0.0);
+    if (p->mode != 1)
+        if (int rc = prepare_rot(p, zeros.data(), st)) return rc;
+    if (int rc = reverse_sweep(p, zeros.data(), p->ket, p->bra, st)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(p->pinned, p->grad_ops, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    p->prof.resolve();
+    CUDA_TRY(cudaGetLastError());
+    for (int j = 0; j < m; ++j) out_host[j] = p->pinned[j];
+    return 0;
 }
 
 // Batched-theta evaluation (API gap i): n_sets parameter vectors evaluated together, one
@@ -1216,6 +1265,44 @@ int tcc_make_rdm12(tcc_plan* p, const double* c_dev, double* rdm1_host, double* 
     return 0;
 }
 
+// pUCCD density-matrix elements on the hard-core-boson CI vector (tencirchem/static/puccd.py:148-203): occ[p] =
+// <n_p>, hop[p,q] = <b+_p b_q> and both[p,q] = <n_p n_q> for q < p (the other triangle is mirrored).  c_dev: the hcb CI
+// vector in reference order on the device.
+int tcc_make_rdm12_hcb(tcc_plan* p, const double* c_dev, double* occ_host, double* hop_host, double* both_host, void* stream) {
+    if (!p || !c_dev || !occ_host || !hop_host || !both_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
+    if (int rc_dev = use_device(p)) return rc_dev;
+    HostPlan& hp = p->hp;
+    if (!hp.hcb) return fail(TCC_ERR_BAD_ARGUMENT, "tcc_make_rdm12_hcb is for hard-core-boson plans (use tcc_make_rdm12)");
+    cudaStream_t st = cudaStream_t(stream);
+    if (int rc = ensure_hcb_tables(p)) return rc;
+    const double* src = c_dev;
+    if (!hp.identity_layout) {
+        if (int rc = ensure_vec(p, &p->ket)) return rc;
+        to_storage(p, c_dev, p->ket, st);
+        src = p->ket;
+    }
+    const int n = hp.n;
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * 2 * size_t(n) * n));
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(double) * 2 * size_t(n) * n, st));
+    launch_hcb_rdm(src, hp.nstr, p->d_strings, n, p->d_binom, n + 2, p->d_bitpos, d_out, d_out + size_t(n) * n, st);
+    p->launches += 1;
+    std::vector<double> out(2 * size_t(n) * n);
+    cudaError_t ce = cudaMemcpyAsync(out.data(), d_out, sizeof(double) * out.size(), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(d_out);
+    if (ce != cudaSuccess) return fail(TCC_ERR_CUDA, cudaGetErrorString(ce));
+    CUDA_TRY(cudaGetLastError());
+    for (int pp = 0; pp < n; ++pp)
+        for (int q = 0; q < n; ++q) {
+            const int hi = std::max(pp, q), lo = std::min(pp, q);
+            hop_host[pp * n + q] = pp == q ? 0.0 : out[size_t(hi) * n + lo];
+            both_host[pp * n + q] = out[size_t(n) * n + size_t(hi) * n + lo];
+        }
+    for (int pp = 0; pp < n; ++pp) occ_host[pp] = out[size_t(n) * n + size_t(pp) * n + pp];
+    return 0;
+}
+
 int tcc_profile_enable(tcc_plan* p, int on) {
     if (!p) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     p->prof.on = on != 0;
@@ -1319,7 +1406,7 @@ int tcc_shard_reverse_interleaved(tcc_plan* p, int seg, double* kb_local_dev, vo
     for (int b = s.batch_hi - 1; b >= s.batch_lo; --b) {
         BatchDevSet& db = p->dbatches[b];
         launch_batch_reverse_il(kb_local_dev, p->hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
-                                SetStrides{0, 0, 0, 0}, st, &p->fan);
+                                SetStrides{0, 0, 0, 0}, st, &p->fan, p->rev_il_mode, p->persist_ctas);
         p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
         p->launches += 2;
     }

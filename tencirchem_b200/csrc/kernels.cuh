@@ -56,4 +56,8 @@ void launch_push_rows(const double* src, int64_t row_doubles, int64_t n_rows, co
 void launch_rdm_gram(const double* c, int64_t na, int64_t nb, const Link* links, int ml, int n, double* gram, int slices,
                      cudaStream_t st);
 
+// hard-core-boson density-matrix elements (puccd.py:148-203): hop[p,q], both[p,q] for q <= p, both[p,p] = occupation
+void launch_hcb_rdm(const double* c, int64_t nstr, const uint32_t* strings, int n, const int64_t* binom, int binom_ld,
+                    const int* bitpos, double* hop, double* both, cudaStream_t st);
+
 }  // namespace tcc

@@ -119,4 +119,68 @@ void launch_rdm_gram(const double* c, int64_t na, int64_t nb, const Link* links,
     rdm_gram_kernel<<<dim3(gx, unsigned(pairs), 1), 256, 0, st>>>(c, na, nb, links, ml, n, n2, gram, n2, n_blocks);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Hard-core-boson (pUCCD) density-matrix elements, tencirchem/static/puccd.py:148-203.  For the pair (p, q) of block
+// blockIdx.x = p * n + q, q <= p, over the strings I of the hcb CI vector (storage order):
+//   p == q:  occ[p]     = sum_I c_I^2 [p in I]
+//   p != q:  hop[p, q]  = sum_I c_I c_{I xor pq} [q in I, p not in I]     (the pair hops from q to p)
+//            both[p, q] = sum_I c_I^2 [p in I and q in I]
+// One block per pair, fixed-order block reduction (deterministic).  The vectors are C(n, k) long: tiny.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hcb_rdm_kernel(const double* __restrict__ c, int64_t nstr, const uint32_t* __restrict__ strings,
+                                                      int n, const int64_t* __restrict__ binom, int binom_ld,
+                                                      const int* __restrict__ bitpos, double* __restrict__ hop,
+                                                      double* __restrict__ both) {
+    __shared__ double red[2][8];
+    const int p = blockIdx.x / n, q = blockIdx.x - p * n;
+    if (q > p) return;
+    const uint32_t mp = 1u << p, mq = 1u << q;
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t i = threadIdx.x; i < nstr; i += 256) {
+        const uint32_t s = strings[i];
+        const double ci = c[i];
+        if (p == q) {
+            if (s & mq) a1 += ci * ci;
+            continue;
+        }
+        if ((s & mq) && (s & mp)) a1 += ci * ci;
+        if ((s & mq) && !(s & mp)) {
+            const uint32_t t = s ^ mp ^ mq;
+            uint32_t tp = 0;
+            for (uint32_t x = t; x; x &= x - 1) tp |= 1u << bitpos[__ffs(x) - 1];
+            int64_t r = 0;
+            int idx = 1;
+            for (uint32_t x = tp; x; x &= x - 1) {
+                r += binom[(__ffs(x) - 1) * binom_ld + idx];
+                ++idx;
+            }
+            a0 += ci * c[r];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = a0;
+        red[1][threadIdx.x >> 5] = a1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            t0 += red[0][w];
+            t1 += red[1][w];
+        }
+        hop[p * n + q] = t0;
+        both[p * n + q] = t1;  // p == q: occ[p]
+    }
+}
+
+void launch_hcb_rdm(const double* c, int64_t nstr, const uint32_t* strings, int n, const int64_t* binom, int binom_ld,
+                    const int* bitpos, double* hop, double* both, cudaStream_t st) {
+    hcb_rdm_kernel<<<unsigned(n * n), 256, 0, st>>>(c, nstr, strings, n, binom, binom_ld, bitpos, hop, both);
+}
+
 }  // namespace tcc

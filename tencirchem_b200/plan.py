@@ -185,6 +185,15 @@ class Plan:
         _lib.check(self.lib.tcc_shard_sigma_ab(self.handle, int(pass_id), self._ptr(c_local), self._ptr(sigma_local),
                                                self._stream()))
 
+    def pool_gradients_dev(self, c, sigma) -> np.ndarray:
+        """<sigma| G_k |c> for every excitation k of this plan (the plan's excitation list is the operator pool);
+        c, sigma: reference-order CI vectors on the device (tcc_pool_gradients)."""
+        self._check_dev(c, "c")
+        self._check_dev(sigma, "sigma")
+        out = np.zeros(max(self.n_ops, 1), dtype=np.float64)
+        _lib.check(self.lib.tcc_pool_gradients(self.handle, self._ptr(c), self._ptr(sigma), _dptr(out), self._stream()))
+        return out[: self.n_ops]
+
     def make_rdm12_dev(self, c):
         """(rdm1 [n, n], rdm2 [n, n, n, n]) of a reference-order CI vector on the device (tcc_make_rdm12)."""
         self._check_dev(c, "c")
@@ -193,6 +202,17 @@ class Plan:
         rdm2 = np.zeros((n, n, n, n), dtype=np.float64)
         _lib.check(self.lib.tcc_make_rdm12(self.handle, self._ptr(c), _dptr(rdm1), _dptr(rdm2), self._stream()))
         return rdm1, rdm2
+
+    def make_rdm12_hcb_dev(self, c):
+        """(occ [n], hop [n, n], both [n, n]) of a reference-order hard-core-boson CI vector on the device
+        (tcc_make_rdm12_hcb, puccd.py:148-203)."""
+        self._check_dev(c, "c")
+        n = self.n_qubits
+        occ = np.zeros(n, dtype=np.float64)
+        hop = np.zeros((n, n), dtype=np.float64)
+        both = np.zeros((n, n), dtype=np.float64)
+        _lib.check(self.lib.tcc_make_rdm12_hcb(self.handle, self._ptr(c), _dptr(occ), _dptr(hop), _dptr(both), self._stream()))
+        return occ, hop, both
 
     def to_storage_order_dev(self, ref, out):
         """out (storage order) <- ref (reference order); full CI vectors on the device."""

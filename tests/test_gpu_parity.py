@@ -500,6 +500,8 @@ def test_adapt_vqe_tutorial_h4_on_the_engine():
         psi = ucc.civector()
         bra = ucc.hamiltonian(psi)
         grads = [2 * sum(bra @ ucc.apply_excitation(psi, op) for op in ops_) for ops_ in pool]
+        # the whole pool in one batched launch set (tcc_pool_gradients), psi and H psi kept on the GPU
+        np.testing.assert_allclose(ucc.pool_gradients(pool), grads, atol=1e-12)
         if it == 0:
             assert abs(np.linalg.norm(grads) - k["h4_adapt_iter0_norm"]) < 2e-7
             pub = {str([list(o) for o in ops_]): g for ops_, g in k["h4_adapt_iter0"]}
@@ -514,6 +516,63 @@ def test_adapt_vqe_tutorial_h4_on_the_engine():
         ucc.init_guess = ucc.params
         ucc.kernel()
         assert abs(ucc.e_ucc - e_pub) < 2e-6, (it, ucc.e_ucc, e_pub)
+
+
+@pytest.mark.parametrize("kind,no,nv", [("uccsd", 3, 3), ("uccsd", 2, 4), ("puccd", 3, 3)])
+def test_pool_gradients_against_oracle(kind, no, nv):
+    """tcc_pool_gradients: 2 <H psi| G_k |psi> for every operator of a pool (all UCCSD excitations, or pUCCD pair
+    excitations on the hard-core-boson space) at a non-trivial state, against the oracle's apply_excitation
+    (evolve_civector.py:311-313) and H psi."""
+    ucc, int1e, int2e = _build(kind, no, nv)
+    params = _params(ucc.n_params)
+    c = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, ucc.hcb)
+    hc = O.get_h_from_integral(int1e, int2e, ucc.n_elec, ucc.hcb)(c)
+    pool = [[op] for op in ucc.ex_ops]
+    ref = np.array([2 * hc @ O.apply_excitation(c, ucc.n_qubits, ucc.n_elec, op, ucc.hcb) for (op,) in pool])
+    got = ucc.pool_gradients(pool, params)
+    assert np.abs(got - ref).max() < G_TOL
+    # grouped entries (operators sharing a parameter) add up
+    pairs = [list(ucc.ex_ops[i:i + 2]) for i in range(0, len(ucc.ex_ops) - 1, 2)]
+    got2 = ucc.pool_gradients(pairs, params)
+    assert np.abs(got2 - np.array([ref[i] + ref[i + 1] for i in range(0, len(ucc.ex_ops) - 1, 2)])).max() < G_TOL
+    O.clear_cache()
+
+
+@pytest.mark.parametrize("no,nv", [(2, 2), (3, 3), (2, 5)])
+def test_puccd_hcb_rdms_on_gpu(no, nv):
+    """tcc_make_rdm12_hcb + PUCCD.make_rdm1 / make_rdm2 against the restated puccd.py:148-203, on an optimiser-free
+    random-theta pUCCD state and on a random hcb vector; and, as in the reference's own test
+    (tests/static/test_puccd.py:48-57), against the fermionic UCC RDMs of the same state built from paired excitations."""
+    from oracle import rdm_numpy as R
+
+    ucc, int1e, int2e = _build("puccd", no, nv)
+    n, ne = no + nv, 2 * no
+    params = _params(ucc.n_params)
+    c = ucc.civector(params)
+    r1, r2 = R.make_rdm12_hcb(c, n, ne)
+    assert np.abs(ucc.make_rdm1(c) - r1).max() < 1e-13
+    assert np.abs(ucc.make_rdm2(c) - r2).max() < 1e-13
+    e = np.einsum("pq,pq", int1e, r1) + 0.5 * np.einsum("pqrs,pqrs", int2e, ucc.make_rdm2(c))
+    assert abs(e - ucc.energy(params)) < E_TOL
+    ucc.params = params
+    assert np.abs(ucc.make_rdm2() - r2).max() < 1e-13  # default: the state at self.params
+    v = np.random.default_rng(3).standard_normal(len(c))
+    a1, a2 = R.make_rdm12_hcb(v, n, ne)
+    assert np.abs(ucc.make_rdm1(v) - a1).max() < 1e-13 * np.abs(a1).max()
+    assert np.abs(ucc.make_rdm2(v) - a2).max() < 1e-13 * np.abs(a2).max()
+    # the same state as a fermionic UCC with paired excitations (b+_i = a+_(n+i) a+_i)
+    from tencirchem_b200 import UCC
+
+    fer = UCC.from_integral(int1e, int2e, ne)
+    fer.ex_ops = tuple((n + a, a, i, n + i) for (a, i) in ucc.ex_ops)
+    fer.param_ids = list(range(len(fer.ex_ops)))
+    fer.params = params
+    assert abs(fer.energy(params) - ucc.energy(params)) < E_TOL
+    assert np.abs(fer.make_rdm1() - ucc.make_rdm1()).max() < 1e-12
+    assert np.abs(fer.make_rdm2() - ucc.make_rdm2()).max() < 1e-12
+    with pytest.raises(ValueError):
+        ucc.make_rdm1(c, basis="AO")
+    O.clear_cache()
 
 
 def test_device_resident_api():

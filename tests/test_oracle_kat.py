@@ -272,6 +272,30 @@ def test_rdm_oracle_against_bruteforce_and_energy_identity():
     assert abs(np.trace(dm1) - ne) < 1e-12
 
 
+@pytest.mark.parametrize("n,ne", [(4, 4), (5, 4), (5, 6)])
+def test_hcb_rdm_oracle_against_the_fermionic_rdm_oracle(n, ne):
+    """oracle make_rdm12_hcb (puccd.py:148-203) against the fermionic RDM oracle on the same state embedded in the
+    full CI space (alpha string == beta string; the pair-creation reordering sign is common to all strings) -- the
+    comparison the reference's own test makes through UCC with paired excitations (tests/static/test_puccd.py:48-57) --
+    plus the energy identity with the hcb Hamiltonian (hamiltonian.py:158-183)."""
+    from oracle import rdm_numpy as R
+
+    int1e, int2e = O.random_integral(n)
+    ns = len(O.make_strings(n, ne // 2))
+    rng = np.random.default_rng(5)
+    c = rng.standard_normal(ns)
+    c /= np.linalg.norm(c)
+    full = np.zeros((ns, ns))
+    full[np.arange(ns), np.arange(ns)] = c
+    f1, f2 = R.make_rdm12(full.ravel(), n, ne)
+    h1, h2 = R.make_rdm12_hcb(c, n, ne)
+    assert np.abs(h1 - f1).max() < 1e-12
+    assert np.abs(h2 - f2).max() < 1e-12
+    h = O.get_h_from_integral(int1e, int2e, ne, True)
+    e = np.einsum("pq,pq", int1e, h1) + 0.5 * np.einsum("pqrs,pqrs", int2e, h2)
+    assert abs(e - c @ h(c)) < 1e-12
+
+
 def test_rdm_oracle_reproduces_the_reference_docstring_example_h2():
     """ucc.py:838-846 (make_rdm2 doctest): for the H2 HF state [1, 0, 0, 0],
     int1e.rdm1 + 1/2 int2e.rdm2 + e_nuc equals the published HF energy."""

@@ -12,6 +12,12 @@
 
 namespace tcc {
 
+#ifdef TCC_DEBUG_SKIP_MEM  // diagnostic build: no tile gather / scatter (the excitations run on whatever shared memory holds)
+#define TCC_MEM_ROWS(n) 0
+#else
+#define TCC_MEM_ROWS(n) (n)
+#endif
+
 constexpr int BK_THREADS = 256;  // upper bound of the launch; the actual block size is a launch parameter
 constexpr int BK_WARPS = BK_THREADS / 32;
 constexpr int BK_DEPTH = 4;  // excitations per prefetch group
@@ -94,9 +100,12 @@ __device__ __forceinline__ double rotate_pairs(double* __restrict__ t0, double* 
 
 template <int NV>
 __global__ void __launch_bounds__(BK_THREADS)
-batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, BatchDev bd, const double2* __restrict__ rot,
-             double* __restrict__ partials, int n_tiles, SetStrides ss, TileRect rect) {
+batch_kernel(double* __restrict__ v0, double* __restrict__ v1, double* __restrict__ vout, int64_t nb, BatchDev bd,
+             const double2* __restrict__ rot, double* __restrict__ partials, int n_tiles, SetStrides ss, TileRect rect) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // vout != null (NV == 1 only): dynamic column layout -- the tile is gathered from v0 with the columns in this batch's
+    // order (B.dyn_in_*) and scattered to vout in the order of the next batch of the sweep (B.dyn_out_*)
+    const bool dyn = NV == 1 && vout != nullptr;
     // blockIdx.y = parameter set (batched-theta evaluation): own vectors, angles and gradient partials
     v0 += int64_t(blockIdx.y) * ss.vec;
     if (NV == 2) v1 += int64_t(blockIdx.y) * ss.vec;
@@ -120,12 +129,19 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
     SmemOp* sops = reinterpret_cast<SmemOp*>(t1 + size_t(nR) * ld);
     double* wpart = reinterpret_cast<double*>(sops + bd.nops);  // [nops][nwarps] (NV == 2)
     uint32_t* row_addr = reinterpret_cast<uint32_t*>(wpart + (NV == 2 ? size_t(bd.nops) * nwarps : 0));  // [nR]
+    uint32_t* ocol = row_addr + nR;                              // [nC] scatter column addresses (dynamic layout)
+    uint16_t* olc = reinterpret_cast<uint16_t*>(ocol + nC);      // [nC] their local columns
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t* addr_a = bd.A.addr + pa.off;
-    const uint32_t* cols_sorted = bd.B.addr_sorted + pb.off;
-    const uint16_t* ord_b = bd.B.ord + pb.off;
+    const uint32_t* cols_sorted = (dyn ? bd.B.dyn_in_sorted : bd.B.addr_sorted) + pb.off;
+    const uint16_t* ord_b = (dyn ? bd.B.dyn_in_ord : bd.B.ord) + pb.off;
     for (int i = tid; i < nR; i += nthreads) row_addr[i] = __ldg(addr_a + i);
+    if (dyn)
+        for (int i = tid; i < nC; i += nthreads) {
+            ocol[i] = __ldg(bd.B.dyn_out_sorted + pb.off + i);
+            olc[i] = __ldg(bd.B.dyn_out_ord + pb.off + i);
+        }
     // each lane owns up to BK_COLCH columns of the tile (ascending global address => coalesced accesses)
     int64_t colg[BK_COLCH];
     int lcs[BK_COLCH];
@@ -180,7 +196,7 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
     if (reg_cols) {
         // asynchronous global->shared copies (LDGSTS): every element of the tile is in flight before the first
         // wait, so the gather costs about one memory latency instead of one per row
-        for (int lr = warp; lr < nR; lr += nwarps) {
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
             const int64_t ra = int64_t(row_addr[lr]) * nb;
 #pragma unroll
             for (int j = 0; j < BK_COLCH; ++j)
@@ -193,7 +209,7 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
         asm volatile("cp.async.wait_all;\n" ::: "memory");
     } else {
         setup_ops();
-        for (int lr = warp; lr < nR; lr += nwarps) {
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
             const int64_t row = int64_t(row_addr[lr]) * nb;
             for (int t = lane; t < nC; t += 32) {
                 const int lc = __ldg(ord_b + t);
@@ -270,7 +286,12 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
             sts64(sh0 + o2, ny);
         };
         fetch(0, cur0, cur1);
-        for (int tb = 0; tb < bd.nops; tb += BK_DEPTH) {
+#ifdef TCC_DEBUG_SKIP_OPS  // diagnostic build: gather / scatter and per-tile set-up only
+        const int nops_loop = 0;
+#else
+        const int nops_loop = bd.nops;
+#endif
+        for (int tb = 0; tb < nops_loop; tb += BK_DEPTH) {
             fetch(tb + BK_DEPTH, nxt0, nxt1);
 #pragma unroll
             for (int j = 0; j < BK_DEPTH; ++j) {
@@ -316,8 +337,13 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
     }
 
     // ---- scatter the tile back
-    if (reg_cols) {
-        for (int lr = warp; lr < nR; lr += nwarps) {
+    if (dyn) {
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
+            double* dst = vout + int64_t(blockIdx.y) * ss.vec + int64_t(row_addr[lr]) * nb;
+            for (int t = lane; t < nC; t += 32) dst[ocol[t]] = t0[lr * ld + olc[t]];
+        }
+    } else if (reg_cols) {
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
             double* dst0 = v0 + int64_t(row_addr[lr]) * nb;
             double* dst1 = NV == 2 ? v1 + int64_t(row_addr[lr]) * nb : nullptr;
 #pragma unroll
@@ -328,7 +354,7 @@ batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, Batch
                 }
         }
     } else {
-        for (int lr = warp; lr < nR; lr += nwarps) {
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
             const int64_t row = int64_t(row_addr[lr]) * nb;
             for (int t = lane; t < nC; t += 32) {
                 const int lc = __ldg(ord_b + t);
@@ -395,8 +421,10 @@ __device__ __forceinline__ double flip_sign(double v, uint32_t flip) {
 
 template <int NV>
 __global__ void __launch_bounds__(BK_THREADS, NV == 1 ? LK_FWD_MINB : 2)
-lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, BatchDev bd, const double2* __restrict__ rot,
-                  double* __restrict__ partials, int n_tiles, SetStrides ss, TileRect rect) {
+lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, double* __restrict__ vout, int64_t nb, BatchDev bd,
+                  const double2* __restrict__ rot, double* __restrict__ partials, int n_tiles, SetStrides ss, TileRect rect) {
+    // vout != null (NV == 1 or 3): dynamic column layout, see batch_kernel
+    const bool dyn = NV != 2 && vout != nullptr;
     constexpr int NVEC = NV == 1 ? 1 : 2;        // vectors rotated
     constexpr int ELW = NV == 3 ? 16 : 8;        // bytes of a tile element in shared memory
     constexpr int ESH = NV == 3 ? 4 : 3;
@@ -425,12 +453,19 @@ lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, 
     uint2* metas = reinterpret_cast<uint2*>(wpart + (NVEC == 2 ? size_t(nops) * nwarps : 0));
     uint32_t* smasks = reinterpret_cast<uint32_t*>(metas + nops);
     uint32_t* row_addr = smasks + nops;
+    uint32_t* ocol = row_addr + nR;                          // [nC] scatter column addresses (dynamic layout)
+    uint16_t* olc = reinterpret_cast<uint16_t*>(ocol + nC);  // [nC] their local columns
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t* addr_a = bd.A.addr + pa.off;
-    const uint32_t* cols_sorted = bd.B.addr_sorted + pb.off;
-    const uint16_t* ord_b = bd.B.ord + pb.off;
+    const uint32_t* cols_sorted = (dyn ? bd.B.dyn_in_sorted : bd.B.addr_sorted) + pb.off;
+    const uint16_t* ord_b = (dyn ? bd.B.dyn_in_ord : bd.B.ord) + pb.off;
     for (int i = tid; i < nR; i += nthreads) row_addr[i] = __ldg(addr_a + i);
+    if (dyn)
+        for (int i = tid; i < nC; i += nthreads) {
+            ocol[i] = __ldg(bd.B.dyn_out_sorted + pb.off + i);
+            olc[i] = __ldg(bd.B.dyn_out_ord + pb.off + i);
+        }
     int64_t colg[BK_COLCH];
     int lcs[BK_COLCH];
     const bool reg_cols = nC <= 32 * BK_COLCH;
@@ -478,7 +513,7 @@ lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, 
     __syncthreads();  // row_addr
     // ---- gather the tile (asynchronous copies: every element is in flight before the first wait)
     if (reg_cols) {
-        for (int lr = warp; lr < nR; lr += nwarps) {
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
             const int64_t ra = int64_t(row_addr[lr]) * nb;
 #pragma unroll
             for (int j = 0; j < BK_COLCH; ++j)
@@ -495,7 +530,7 @@ lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, 
         asm volatile("cp.async.wait_all;\n" ::: "memory");
     } else {
         setup_ops();
-        for (int lr = warp; lr < nR; lr += nwarps) {
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
             const int64_t row = int64_t(row_addr[lr]) * nb;
             for (int t = lane; t < nC; t += 32) {
                 const int lc = __ldg(ord_b + t);
@@ -562,7 +597,12 @@ lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, 
             }
         };
         fetch(0, cur0, cur1);
-        for (int tb = 0; tb < nops; tb += LK_DEPTH) {
+#ifdef TCC_DEBUG_SKIP_OPS  // diagnostic build: gather / scatter and per-tile set-up only
+        const int nops_loop = 0;
+#else
+        const int nops_loop = nops;
+#endif
+        for (int tb = 0; tb < nops_loop; tb += LK_DEPTH) {
             fetch(tb + LK_DEPTH, nxt0, nxt1);
 #pragma unroll
             for (int j = 0; j < LK_DEPTH; ++j) {
@@ -619,8 +659,19 @@ lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, 
     }
 
     // ---- scatter the tile back
-    if (reg_cols) {
-        for (int lr = warp; lr < nR; lr += nwarps) {
+    if (dyn) {
+        double* outv = vout + int64_t(blockIdx.y) * ss.vec;
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
+            const int64_t ra = int64_t(row_addr[lr]) * nb;
+            for (int t = lane; t < nC; t += 32) {
+                if (NV == 3)
+                    reinterpret_cast<double2*>(outv)[ra + ocol[t]] = reinterpret_cast<const double2*>(t0)[lr * ld + olc[t]];
+                else
+                    outv[ra + ocol[t]] = reinterpret_cast<const double*>(t0)[lr * ld + olc[t]];
+            }
+        }
+    } else if (reg_cols) {
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
             const int64_t ra = int64_t(row_addr[lr]) * nb;
 #pragma unroll
             for (int j = 0; j < BK_COLCH; ++j)
@@ -634,7 +685,7 @@ lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, 
                 }
         }
     } else {
-        for (int lr = warp; lr < nR; lr += nwarps) {
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
             const int64_t row = int64_t(row_addr[lr]) * nb;
             for (int t = lane; t < nC; t += 32) {
                 const int lc = __ldg(ord_b + t);
@@ -660,326 +711,6 @@ lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, int64_t nb, 
     }
 }
 
-// ================================================================================================================
-// Reverse sweep on interleaved (ket, bra) elements, second generation (rev_il_kernel).  Same tiles, streams, arithmetic
-// and order of excitations as lean_batch_kernel<3>; what changes is the latency structure (the ncu capture of
-// lean_batch_kernel<3> showed nothing saturated at 2 CTAs per SM: the kernel waits):
-//   * PERSISTENT: a CTA walks over tiles (tile = blockIdx.x + k * gridDim.x).  The panel descriptors of the NEXT tile
-//     are requested while the gather of the current one is in flight, its row / column address tables while the
-//     excitations run, so the three dependent global loads in front of every gather disappear from the critical path;
-//   * the two pairs a thread applies per excitation are loaded together before either is rotated (they are disjoint):
-//     one shared-memory latency per excitation instead of two;
-//   * the (cos, sin) records and stream offsets of a group of four excitations are read by a few wide loads at the
-//     start of the group instead of one dependent load per excitation.
-// gridDim.x == number of tiles gives the one-tile-per-CTA behaviour with the same code.
-// ================================================================================================================
-struct RevIlGeom {  // per-tile quantities derived from the two panel descriptors
-    int nR, nC, ld, tps, lid, sbase, sshift_a, sshift_b;
-    bool active, multi, reg_cols;
-};
-
-__device__ __forceinline__ RevIlGeom rev_il_geom(const PanelDesc& pa, const PanelDesc& pb, int tid, int nthreads) {
-    RevIlGeom g;
-    g.nR = int(pa.G) * int(pa.c);
-    g.nC = int(pb.G) * int(pb.c);
-    g.ld = int(pb.ld);
-    const int Gan = max(1, int(pa.Gn)), Gbn = max(1, int(pb.Gn));
-    const int nsub = Gan * Gbn;
-    g.tps = nthreads / nsub;
-    const int sub = tid / g.tps;
-    const int ga = sub / Gbn, gb = sub - ga * Gbn;
-    g.active = sub < nsub && ga < int(pa.G) && gb < int(pb.G);
-    g.lid = tid - sub * g.tps;
-    g.sbase = g.active ? ga * int(pa.c) * g.ld + gb * int(pb.c) : 0;
-    g.sshift_a = ga;
-    g.sshift_b = 16 + gb;
-    g.multi = nsub > 1;
-    g.reg_cols = g.nC <= 32 * BK_COLCH;
-    return g;
-}
-
-__global__ void __launch_bounds__(BK_THREADS, 2)
-rev_il_kernel(double* __restrict__ kb, int64_t nb, BatchDev bd, const double2* __restrict__ rot, double* __restrict__ partials,
-              int n_tiles, SetStrides ss, TileRect rect, int tile_bytes_max, int max_rows) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    kb += int64_t(blockIdx.y) * ss.vec;
-    rot += int64_t(blockIdx.y) * ss.rot;
-    partials += int64_t(blockIdx.y) * ss.part;
-    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-    const int nops = bd.nops;
-    const int nops4 = (nops + 3) & ~3;
-    // shared memory (offsets fixed by the launch maxima: a CTA sees tiles of several sizes):
-    // tile | records [nops4] | warp partials [nops][nwarps] | meta [nops4 + 4] | spectator masks [nops4] | row addresses [2][max_rows]
-    unsigned char* t0 = smem_raw;
-    double2* recs = reinterpret_cast<double2*>(t0 + tile_bytes_max);
-    double* wpart = reinterpret_cast<double*>(recs + nops4);
-    uint2* metas = reinterpret_cast<uint2*>(wpart + size_t(nops) * nwarps + (size_t(nops) * nwarps & 1));
-    uint32_t* smasks = reinterpret_cast<uint32_t*>(metas + nops4 + 4);
-    uint32_t* row_addr = smasks + nops4;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rect_tiles = rect.pa_cnt * rect.pb_cnt;
-    int tile_lin = blockIdx.x;
-    if (tile_lin >= rect_tiles) return;
-
-    auto tile_panels = [&](int lin, PanelDesc* pa, PanelDesc* pb, int* tile_id) {
-        const int pa_loc = lin / rect.pb_cnt;
-        const int pa_id = rect.pa_lo + pa_loc, pb_id = rect.pb_lo + (lin - pa_loc * rect.pb_cnt);
-        *pa = bd.A.panels[pa_id];
-        *pb = bd.B.panels[pb_id];
-        *tile_id = pa_id * bd.B.n_panels + pb_id;
-    };
-    PanelDesc pa, pb;
-    int tile_id;
-    tile_panels(tile_lin, &pa, &pb, &tile_id);
-    uint32_t colg[BK_COLCH];
-    int lcs[BK_COLCH];
-    auto load_cols = [&](const PanelDesc& pbx, uint32_t* cg, int* lc) {
-        const int nC = int(pbx.G) * int(pbx.c);
-        const uint32_t* cols_sorted = bd.B.addr_sorted + pbx.off;
-        const uint16_t* ord_b = bd.B.ord + pbx.off;
-#pragma unroll
-        for (int j = 0; j < BK_COLCH; ++j) {
-            const int t = lane + 32 * j;
-            cg[j] = 0;
-            lc[j] = -1;
-            if (nC <= 32 * BK_COLCH && t < nC) {
-                cg[j] = __ldg(cols_sorted + t);
-                lc[j] = __ldg(ord_b + t);
-            }
-        }
-    };
-    load_cols(pb, colg, lcs);
-    for (int i = tid; i < int(pa.G) * int(pa.c); i += nthreads) row_addr[i] = __ldg(bd.A.addr + pa.off + i);
-    // pad entries of the meta table: the prefetch of the group after the last one reads them
-    if (tid < 4) metas[nops4 + tid] = make_uint2(0u, 0u);
-    __syncthreads();
-
-    const uint32_t sh_tile = uint32_t(__cvta_generic_to_shared(t0));
-    const uint32_t rec_s = uint32_t(__cvta_generic_to_shared(recs));
-    const uint32_t meta_s = uint32_t(__cvta_generic_to_shared(metas));
-    const uint32_t mask_s = uint32_t(__cvta_generic_to_shared(smasks));
-    const uint32_t* __restrict__ stream = bd.stream16;
-
-    for (int it = 0;; ++it) {
-        const uint32_t* ra_cur = row_addr + (it & 1) * max_rows;
-        uint32_t* ra_nxt = row_addr + ((it & 1) ^ 1) * max_rows;
-        const RevIlGeom g = rev_il_geom(pa, pb, tid, nthreads);
-        const int ld = g.ld;
-        // ---- gather (asynchronous copies, 16 bytes per element)
-        if (g.reg_cols) {
-            for (int lr = warp; lr < g.nR; lr += nwarps) {
-                const int64_t ra = int64_t(ra_cur[lr]) * nb;
-#pragma unroll
-                for (int j = 0; j < BK_COLCH; ++j)
-                    if (lcs[j] >= 0) cp_async16(t0 + (size_t(lr) * ld + lcs[j]) * 16, kb + (ra + colg[j]) * 2);
-            }
-        }
-        // ---- descriptors of the next tile: requested now, used after the gather has landed
-        const int next_lin = tile_lin + int(gridDim.x);
-        const bool has_next = next_lin < rect_tiles;
-        PanelDesc pa_n = pa, pb_n = pb;
-        int tile_id_n = tile_id;
-        if (has_next) tile_panels(next_lin, &pa_n, &pb_n, &tile_id_n);
-        // ---- excitation records of this tile
-        for (int t = tid; t < nops4; t += nthreads) {
-            uint2 meta = make_uint2(0u, 0u);
-            uint32_t smask = 0;
-            double2 rec = make_double2(1.0, 0.0);
-            if (t < nops) {
-                const BatchOp op = bd.ops[t];
-                const int fwd_pos = bd.reversed ? nops - 1 - t : t;
-                const int* si = bd.stream_index + ((size_t(fwd_pos) * (bd.A.m + 1) + int(pa.e)) * (bd.B.m + 1) + int(pb.e)) * 2;
-                meta = make_uint2(uint32_t(si[0]), uint32_t(si[1]));
-                if (op.h_a >= 0)
-                    for (int q = 0; q < int(pa.G); ++q) smask |= (uint32_t(__popc(bd.A.sigma[pa.class_off + q] & op.zspec_a)) & 1u) << q;
-                if (op.h_b >= 0)
-                    for (int q = 0; q < int(pb.G); ++q) smask |= (uint32_t(__popc(bd.B.sigma[pb.class_off + q] & op.zspec_b)) & 1u) << (16 + q);
-                const double2 cs = __ldg(rot + op.op_index);
-                const bool fold = !g.multi && (((smask ^ (smask >> 16)) & 1u) != 0);
-                rec = make_double2(cs.x, fold ? -cs.y : cs.y);
-            }
-            recs[t] = rec;
-            metas[t] = meta;
-            smasks[t] = smask;
-        }
-        if (!g.reg_cols) {  // wide tiles: plain loads (rare)
-            const uint32_t* cols_sorted = bd.B.addr_sorted + pb.off;
-            const uint16_t* ord_b = bd.B.ord + pb.off;
-            for (int lr = warp; lr < g.nR; lr += nwarps) {
-                const int64_t row = int64_t(ra_cur[lr]) * nb;
-                for (int t = lane; t < g.nC; t += 32)
-                    reinterpret_cast<double2*>(t0)[lr * ld + __ldg(ord_b + t)] = reinterpret_cast<const double2*>(kb)[row + __ldg(cols_sorted + t)];
-            }
-        }
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
-        __syncthreads();
-        // ---- address tables of the next tile: requested now (registers), parked in shared memory after the first group
-        uint32_t colg_n[BK_COLCH];
-        int lcs_n[BK_COLCH];
-        uint32_t ra_n = 0;
-        const int nR_n = int(pa_n.G) * int(pa_n.c);
-        if (has_next) {
-            load_cols(pb_n, colg_n, lcs_n);
-            if (tid < nR_n) ra_n = __ldg(bd.A.addr + pa_n.off + tid);
-        }
-
-        // ---- the excitations of the batch, in order
-        {
-            const uint32_t* __restrict__ sp = stream + g.lid;
-            const uint32_t sh0 = sh_tile + (uint32_t(g.sbase) << 4);
-            const int tps = g.tps;
-            uint32_t cur0[LK_DEPTH], cur1[LK_DEPTH], nxt0[LK_DEPTH], nxt1[LK_DEPTH];
-            double accs[LK_DEPTH];
-            auto fetch = [&](int tbase, uint32_t* e0, uint32_t* e1) {
-                // four (offset, slots) records by two wide loads, then up to eight independent entry loads
-                const double2 ma = lds128(meta_s + tbase * 8), mb = lds128(meta_s + tbase * 8 + 16);
-                const uint32_t off[4] = {uint32_t(__double2loint(ma.x)), uint32_t(__double2loint(ma.y)), uint32_t(__double2loint(mb.x)),
-                                         uint32_t(__double2loint(mb.y))};
-                const uint32_t sl[4] = {uint32_t(__double2hiint(ma.x)), uint32_t(__double2hiint(ma.y)), uint32_t(__double2hiint(mb.x)),
-                                        uint32_t(__double2hiint(mb.y))};
-#pragma unroll
-                for (int j = 0; j < LK_DEPTH; ++j) {
-                    e0[j] = 0;
-                    e1[j] = 0;
-                    if (g.active) {
-                        if (sl[j] > 0) e0[j] = __ldg(sp + off[j]);
-                        if (sl[j] > 1) e1[j] = __ldg(sp + off[j] + tps);
-                    }
-                }
-            };
-            auto rotate = [&](uint32_t o1, uint32_t o2, const double2& a, const double2& b, double cs, double sn, uint32_t flip, double& acc) {
-                const double p = flip_sign(sn, flip);
-                // <bra|G|ket> of the pair is invariant under the common rotation: taken from the values before it
-                acc = fma(flip_sign(a.y, flip), b.x, acc);
-                acc = fma(-flip_sign(b.y, flip), a.x, acc);
-                sts128(sh0 + o1, cs * a.x + p * b.x, cs * a.y + p * b.y);
-                sts128(sh0 + o2, cs * b.x - p * a.x, cs * b.y - p * a.y);
-            };
-            fetch(0, cur0, cur1);
-            for (int tb = 0; tb < nops; tb += LK_DEPTH) {
-                // records of this group (consumed by its first excitation about one shared-memory latency later)
-                double2 r4[LK_DEPTH];
-                uint32_t sm4[LK_DEPTH];
-#pragma unroll
-                for (int j = 0; j < LK_DEPTH; ++j) {
-                    r4[j] = lds128(rec_s + (tb + j) * 16);
-                    sm4[j] = g.multi ? lds32u(mask_s + (tb + j) * 4) : 0u;
-                }
-                fetch(tb + LK_DEPTH, nxt0, nxt1);
-#pragma unroll
-                for (int j = 0; j < LK_DEPTH; ++j) {
-                    const int t = tb + j;
-                    accs[j] = 0.0;
-                    if (t < nops) {
-                        const uint32_t e0 = cur0[j], e1 = cur1[j];
-                        if (e0 & LK_VALID) {  // an entry in round 1 implies one in round 0
-                            const uint32_t sflip = g.multi ? ((sm4[j] >> g.sshift_a) ^ (sm4[j] >> g.sshift_b)) << 31 : 0u;
-                            const double cs = r4[j].x, sn = r4[j].y;
-                            double acc = 0.0;
-                            const uint32_t o1 = (e0 & 0x7fffu) << 4, o2 = (e0 >> 11) & 0x7fff0u;
-                            const uint32_t f0 = ((e0 << 1) & 0x80000000u) ^ sflip;
-                            const double2 a0 = lds128(sh0 + o1), b0 = lds128(sh0 + o2);
-                            if (e1 & LK_VALID) {
-                                // the second pair of the thread is disjoint from the first: both are loaded before either is stored
-                                const uint32_t o3 = (e1 & 0x7fffu) << 4, o4 = (e1 >> 11) & 0x7fff0u;
-                                const uint32_t f1 = ((e1 << 1) & 0x80000000u) ^ sflip;
-                                const double2 a1 = lds128(sh0 + o3), b1 = lds128(sh0 + o4);
-                                rotate(o1, o2, a0, b0, cs, sn, f0, acc);
-                                rotate(o3, o4, a1, b1, cs, sn, f1, acc);
-                                const uint2 m = lds64u(meta_s + t * 8);
-                                for (uint32_t s_ = 2; s_ < m.y; ++s_) {
-                                    const uint32_t e = __ldg(sp + m.x + s_ * tps);
-                                    if (e & LK_VALID) {
-                                        const uint32_t q1 = (e & 0x7fffu) << 4, q2 = (e >> 11) & 0x7fff0u;
-                                        const double2 a = lds128(sh0 + q1), b = lds128(sh0 + q2);
-                                        rotate(q1, q2, a, b, cs, sn, ((e << 1) & 0x80000000u) ^ sflip, acc);
-                                    }
-                                }
-                            } else {
-                                rotate(o1, o2, a0, b0, cs, sn, f0, acc);
-                            }
-                            accs[j] = acc;
-                        }
-                        __syncthreads();
-                    }
-                }
-                {
-                    // transposed butterfly (see lean_batch_kernel)
-                    const bool hi16 = lane & 16, hi8 = lane & 8;
-                    const double s0 = hi16 ? accs[0] : accs[2], s1 = hi16 ? accs[1] : accs[3];
-                    double k0 = (hi16 ? accs[2] : accs[0]) + __shfl_xor_sync(0xffffffffu, s0, 16);
-                    double k1 = (hi16 ? accs[3] : accs[1]) + __shfl_xor_sync(0xffffffffu, s1, 16);
-                    double k = (hi8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
-                    k += __shfl_xor_sync(0xffffffffu, k, 4);
-                    k += __shfl_xor_sync(0xffffffffu, k, 2);
-                    k += __shfl_xor_sync(0xffffffffu, k, 1);
-                    if ((lane & 7) == 0) {
-                        const int j = ((lane >> 4) << 1) | ((lane >> 3) & 1);
-                        if (tb + j < nops) wpart[(tb + j) * nwarps + warp] = k;
-                    }
-                }
-                if (tb == 0 && has_next && tid < nR_n) ra_nxt[tid] = ra_n;  // nobody reads this buffer during this tile
-#pragma unroll
-                for (int j = 0; j < LK_DEPTH; ++j) {
-                    cur0[j] = nxt0[j];
-                    cur1[j] = nxt1[j];
-                }
-            }
-            if (nops == 0 && has_next && tid < nR_n) ra_nxt[tid] = ra_n;
-        }
-
-        // ---- scatter the tile back
-        if (g.reg_cols) {
-            for (int lr = warp; lr < g.nR; lr += nwarps) {
-                const int64_t ra = int64_t(ra_cur[lr]) * nb;
-                double2 v[BK_COLCH];
-#pragma unroll
-                for (int j = 0; j < BK_COLCH; ++j)
-                    if (lcs[j] >= 0) v[j] = reinterpret_cast<const double2*>(t0)[lr * ld + lcs[j]];
-#pragma unroll
-                for (int j = 0; j < BK_COLCH; ++j)
-                    if (lcs[j] >= 0) reinterpret_cast<double2*>(kb)[ra + colg[j]] = v[j];
-            }
-        } else {
-            const uint32_t* cols_sorted = bd.B.addr_sorted + pb.off;
-            const uint16_t* ord_b = bd.B.ord + pb.off;
-            for (int lr = warp; lr < g.nR; lr += nwarps) {
-                const int64_t row = int64_t(ra_cur[lr]) * nb;
-                for (int t = lane; t < g.nC; t += 32)
-                    reinterpret_cast<double2*>(kb)[row + __ldg(cols_sorted + t)] = reinterpret_cast<const double2*>(t0)[lr * ld + __ldg(ord_b + t)];
-            }
-        }
-        __syncthreads();
-        for (int t = tid; t < nops; t += nthreads) {
-            double s = 0.0;
-            for (int w = 0; w < nwarps; ++w) s += wpart[t * nwarps + w];
-            if (!g.multi && (((smasks[t] ^ (smasks[t] >> 16)) & 1u) != 0)) s = -s;
-            partials[int64_t(t) * n_tiles + tile_id] = s;
-        }
-        if (!has_next) break;
-        __syncthreads();  // tile, records and partials are free again; the next row addresses are visible
-        pa = pa_n;
-        pb = pb_n;
-        tile_id = tile_id_n;
-        tile_lin = next_lin;
-#pragma unroll
-        for (int j = 0; j < BK_COLCH; ++j) {
-            colg[j] = colg_n[j];
-            lcs[j] = lcs_n[j];
-        }
-    }
-}
-
-size_t rev_il_smem_bytes(int max_rows, int max_cols, int nops, int* tile_bytes_max) {
-    const size_t ld = size_t(max_cols) | 1;
-    const size_t tile = (size_t(max_rows) * ld * 16 + 15) & ~size_t(15);
-    *tile_bytes_max = int(tile);
-    const size_t nops4 = (size_t(nops) + 3) & ~size_t(3);
-    size_t wp = size_t(nops) * BK_WARPS;
-    wp += wp & 1;
-    return tile + nops4 * 16 + wp * 8 + (nops4 + 4) * 8 + nops4 * 4 + 2 * size_t(max_rows) * 4 + 32;
-}
-
 size_t lean_smem_bytes(int max_rows, int max_cols, int nops, int nv) {
     const size_t ld = size_t(max_cols) | 1;
     const size_t elw = nv == 3 ? 16 : 8;
@@ -988,6 +719,7 @@ size_t lean_smem_bytes(int max_rows, int max_cols, int nops, int nv) {
     if (nv >= 2) bytes += size_t(nops) * BK_WARPS * sizeof(double);  // warp partials
     bytes += size_t(nops) * 8 + size_t(nops) * 4;                 // meta, spectator masks
     bytes += size_t(max_rows) * sizeof(uint32_t);
+    bytes += size_t(max_cols) * 6 + 8;  // scatter tables of the dynamic column layout
     return bytes + 16;
 }
 
@@ -1042,6 +774,7 @@ size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv) {
     bytes += size_t(nops) * sizeof(SmemOp);
     if (nv == 2) bytes += size_t(nops) * BK_WARPS * sizeof(double);
     bytes += size_t(max_rows) * sizeof(uint32_t);
+    bytes += size_t(max_cols) * 6 + 8;  // scatter tables of the dynamic column layout
     return bytes + 16;
 }
 
@@ -1051,7 +784,6 @@ cudaError_t batch_kernels_configure() {
     if ((e = cudaFuncSetAttribute(lean_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lean_batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lean_batch_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(rev_il_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
@@ -1107,15 +839,16 @@ static void fan_out(const std::vector<TileRect>& rects, cudaStream_t st, StreamF
         }
 }
 
-void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
+// v_out: null = in place (static column order); otherwise out of place with the dynamic column layout (BatchDev::B.dyn_*)
+void launch_batch_forward(double* v, double* v_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
                           int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan) {
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
         if (grid.x == 0) return;  // a rank of a sharded plan may own no class of this batch
         if (bd.lean)
-            lean_batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss, r);
+            lean_batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, v_out, nb, bd, rot, nullptr, 0, ss, r);
         else
-            batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, nb, bd, rot, nullptr, 0, ss, r);
+            batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, v_out, nb, bd, rot, nullptr, 0, ss, r);
     });
 }
 
@@ -1127,30 +860,23 @@ void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& 
         dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
         if (grid.x == 0) return;
         if (bd.lean)
-            lean_batch_kernel<2><<<grid, threads, r.smem_rev, s>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss, r);
+            lean_batch_kernel<2><<<grid, threads, r.smem_rev, s>>>(ket, bra, nullptr, nb, bd, rot, partials, n_tiles, ss, r);
         else
-            batch_kernel<2><<<grid, threads, r.smem_rev, s>>>(ket, bra, nb, bd, rot, partials, n_tiles, ss, r);
+            batch_kernel<2><<<grid, threads, r.smem_rev, s>>>(ket, bra, nullptr, nb, bd, rot, partials, n_tiles, ss, r);
     });
     batch_grad_reduce_kernel<<<dim3(bd.nops, unsigned(n_sets), 1), 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops, ss);
 }
 
-// reverse sweep of one batch on interleaved (ket, bra) elements: kb = [rows][nb][2].
-// mode 0: lean_batch_kernel<3> (one tile per CTA); 1: rev_il_kernel, one tile per CTA; 2: rev_il_kernel, persistent
-// (`persist_ctas` CTAs walk over the tiles)
-void launch_batch_reverse_il(double* kb, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan,
-                             int mode, int persist_ctas) {
+// reverse sweep of one batch on interleaved (ket, bra) elements: kb = [rows][nb][2].  kb_out: null = in place in the
+// static column order; otherwise the batch reads kb with its columns in the batch's own order and writes kb_out in the
+// order of the next batch of the sweep (BatchDev::B.dyn_*, dynamic column layout)
+void launch_batch_reverse_il(double* kb, double* kb_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
+                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan) {
     const int n_tiles = bd.B.n_panels * bd.A.n_panels;
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         const unsigned tiles = unsigned(r.pa_cnt) * unsigned(r.pb_cnt);
         if (tiles == 0) return;
-        if (mode == 0 || r.max_rows > threads) {
-            lean_batch_kernel<3><<<dim3(tiles, unsigned(n_sets), 1), threads, r.smem_il, s>>>(kb, nullptr, nb, bd, rot, partials, n_tiles, ss, r);
-            return;
-        }
-        const unsigned ctas = mode == 2 ? std::min<unsigned>(tiles, unsigned(std::max(1, persist_ctas))) : tiles;
-        rev_il_kernel<<<dim3(ctas, unsigned(n_sets), 1), threads, r.smem_il2, s>>>(kb, nb, bd, rot, partials, n_tiles, ss, r, r.tile_bytes_il2,
-                                                                                 r.max_rows);
+        lean_batch_kernel<3><<<dim3(tiles, unsigned(n_sets), 1), threads, r.smem_il, s>>>(kb, nullptr, kb_out, nb, bd, rot, partials, n_tiles, ss, r);
     });
     batch_grad_reduce_kernel<<<dim3(bd.nops, unsigned(n_sets), 1), 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops, ss);
 }

@@ -20,6 +20,11 @@ struct SideDev {
     const int32_t* tab_index;
     int m;
     int n_panels;
+    // dynamic column layout (beta side, null without it): gather / scatter tables of this sweep direction
+    const uint32_t* dyn_in_sorted;
+    const uint16_t* dyn_in_ord;
+    const uint32_t* dyn_out_sorted;
+    const uint16_t* dyn_out_ord;
 };
 
 struct BatchDev {
@@ -49,9 +54,7 @@ struct TileRect {
     int pa_lo, pa_cnt, pb_lo, pb_cnt;
     size_t smem_fwd, smem_rev;
     size_t smem_il;   // reverse sweep on interleaved (ket, bra) elements (lean_batch_kernel<3>)
-    size_t smem_il2;  // the same for rev_il_kernel
-    int tile_bytes_il2;
-    int max_rows;
+    int max_rows, max_cols;
 };
 
 // Auxiliary streams for the rectangle launches of one batch: the rectangles are independent sets of tiles, so they
@@ -67,13 +70,11 @@ struct StreamFan {
 cudaError_t batch_kernels_configure();
 size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv);
 size_t lean_smem_bytes(int max_rows, int max_cols, int nops, int nv);
-size_t rev_il_smem_bytes(int max_rows, int max_cols, int nops, int* tile_bytes_max);
-void launch_batch_reverse_il(double* kb, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan,
-                             int mode, int persist_ctas);
+void launch_batch_reverse_il(double* kb, double* kb_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
+                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan);
 void launch_interleave(const double* a, const double* b, double* out, int64_t n, cudaStream_t st);
 void launch_deinterleave(const double* in, double* a, double* b, int64_t n, cudaStream_t st);
-void launch_batch_forward(double* v, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
+void launch_batch_forward(double* v, double* v_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
                           int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan);
 void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot,
                           const std::vector<TileRect>& rects, int threads, double* partials, double* grad_ops, int n_sets,

@@ -145,8 +145,12 @@ struct tcc_plan {
     int lean = 1;           // lean per-thread streams for two-sided batches (TCC_B200_LEAN=0: the plain pair lists)
     int lean_fwd = 0;       // forward sweep on the lean kernel too (TCC_B200_LEAN_FWD=1); measured slower than batch_kernel<1>
     int rev_interleave = 1; // reverse sweep on interleaved (ket, bra) elements (TCC_B200_REV_IL=0: two vectors)
-    int rev_il_mode = 2;    // 0: lean_batch_kernel<3>; 1: rev_il_kernel, one tile per CTA; 2: rev_il_kernel, persistent
-    int persist_ctas = 296; // CTAs of the persistent launch (2 per SM)
+    int dyn = 0;            // dynamic column layout (plan.hpp, TCC_B200_DYN_LAYOUT=1; off by default: measured no faster and it takes
+                            // three more vectors): out-of-place sweeps, every batch gathers contiguous columns
+    double* dyn_f = nullptr;   // second buffer of the forward sweep [N]
+    double* kb2 = nullptr;     // second buffer of the interleaved reverse sweep [2 N]
+    uint32_t* d_dyn_init = nullptr;  // [nstr] column map reference order -> first forward layout (init_state)
+    int64_t hf_index_dyn = 0;
     double* io1 = nullptr;  // reference-order staging for the host-buffer entry points
     double* io2 = nullptr;
     double* partials = nullptr;
@@ -257,7 +261,21 @@ static int upload_batches(tcc_plan* p) {
             CUDA_TRY(dev_upload(p, hb.stream_index, &db.fwd.stream_index, &db.allocs));
             db.fwd.lean = 1;
         }
+        db.fwd.B.dyn_in_sorted = db.fwd.B.dyn_out_sorted = nullptr;
+        db.fwd.B.dyn_in_ord = db.fwd.B.dyn_out_ord = nullptr;
+        db.fwd.A.dyn_in_sorted = db.fwd.A.dyn_out_sorted = nullptr;
+        db.fwd.A.dyn_in_ord = db.fwd.A.dyn_out_ord = nullptr;
         db.rev = db.fwd;
+        if (hp.dyn_layout) {
+            CUDA_TRY(dev_upload(p, hb.dyn_fwd_in.addr_sorted, &db.fwd.B.dyn_in_sorted, &db.allocs));
+            CUDA_TRY(dev_upload(p, hb.dyn_fwd_in.ord, &db.fwd.B.dyn_in_ord, &db.allocs));
+            CUDA_TRY(dev_upload(p, hb.dyn_fwd_out.addr_sorted, &db.fwd.B.dyn_out_sorted, &db.allocs));
+            CUDA_TRY(dev_upload(p, hb.dyn_fwd_out.ord, &db.fwd.B.dyn_out_ord, &db.allocs));
+            CUDA_TRY(dev_upload(p, hb.dyn_rev_in.addr_sorted, &db.rev.B.dyn_in_sorted, &db.allocs));
+            CUDA_TRY(dev_upload(p, hb.dyn_rev_in.ord, &db.rev.B.dyn_in_ord, &db.allocs));
+            CUDA_TRY(dev_upload(p, hb.dyn_rev_out.addr_sorted, &db.rev.B.dyn_out_sorted, &db.allocs));
+            CUDA_TRY(dev_upload(p, hb.dyn_rev_out.ord, &db.rev.B.dyn_out_ord, &db.allocs));
+        }
         db.fwd.lean = db.fwd.lean && p->lean_fwd;
         db.rev.reversed = 1;
         std::vector<BatchOp> rev_ops(hb.ops.rbegin(), hb.ops.rend());
@@ -315,8 +333,7 @@ static int upload_batches(tcc_plan* p) {
                     r.smem_rev = db.rev.lean ? lean_smem_bytes(xa[2], cols, db.nops, 2) : batch_smem_bytes(xa[2], cols, db.nops, 2);
                     r.smem_il = db.rev.lean ? lean_smem_bytes(xa[2], cols, db.nops, 3) : 0;
                     r.max_rows = xa[2];
-                    r.tile_bytes_il2 = 0;
-                    r.smem_il2 = db.rev.lean ? rev_il_smem_bytes(xa[2], cols, db.nops, &r.tile_bytes_il2) : 0;
+                    r.max_cols = cols;
                     db.smem_fwd = std::max(db.smem_fwd, r.smem_fwd);
                     db.smem_rev = std::max(db.smem_rev, r.smem_rev);
                     if (r.pa_cnt > 0 && r.pb_cnt > 0) out->push_back(r);
@@ -324,7 +341,7 @@ static int upload_batches(tcc_plan* p) {
         };
         make_rects(split >= 2, &db.rects);
         make_rects(split >= 1, &db.rects_rev);
-        for (const TileRect& r : db.rects_rev) db.smem_rev = std::max(db.smem_rev, std::max(r.smem_il, r.smem_il2));
+        for (const TileRect& r : db.rects_rev) db.smem_rev = std::max(db.smem_rev, r.smem_il);
         if (db.smem_rev > 232448)
             return fail(TCC_ERR_BAD_ARGUMENT, "batch tile does not fit in shared memory: lower TCC_B200_TILE_ELEMS");
         max_part = std::max(max_part, size_t(db.nops) * size_t(db.n_tiles));
@@ -444,9 +461,9 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
               p->batch_threads >= 64;
     p->rev_interleave = p->lean && env_int("TCC_B200_REV_IL", 1) != 0;
     p->lean_fwd = p->lean && env_int("TCC_B200_LEAN_FWD", 0) != 0;
-    p->rev_il_mode = env_int("TCC_B200_REV_IL_MODE", 2);
     p->hp.error.clear();
-    p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0, rank, world, p->lean ? p->batch_threads : 0);
+    p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0, rank, world, p->lean ? p->batch_threads : 0,
+                   env_int("TCC_B200_DYN_LAYOUT", 0) != 0 && world == 1);
     if (!p->hp.error.empty()) {
         g_error = p->hp.error;
         delete p;
@@ -478,11 +495,6 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
         return code;
     };
     if (int rc_dev = use_device(p)) return bail(rc_dev);
-    {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        p->persist_ctas = env_int("TCC_B200_PERSIST_CTAS", 2 * sms);
-    }
     for (size_t h = 0; h < p->hp.hops.size(); ++h)
         if (upload_hop(p, int(h))) return bail(TCC_ERR_CUDA);
     if (int rc2 = upload_batches(p)) return bail(rc2);
@@ -502,6 +514,20 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
     }
     cudaMemcpy(p->d_ref2int, p->hp.ref2int.data(), sizeof(uint32_t) * p->hp.nstr, cudaMemcpyHostToDevice);
     cudaMemcpy(p->d_int2ref, p->hp.int2ref.data(), sizeof(uint32_t) * p->hp.nstr, cudaMemcpyHostToDevice);
+    if (p->hp.dyn_layout) {
+        // column c' of the first forward layout holds the string with static address inv[c'], reference address int2ref[inv[c']]
+        const HostPlan& hp = p->hp;
+        std::vector<uint32_t> init_map(size_t(hp.nstr));
+        for (int64_t a = 0; a < hp.nstr; ++a) init_map[hp.dyn_col0[a]] = hp.int2ref[a];
+        if (cudaMalloc(&p->d_dyn_init, sizeof(uint32_t) * hp.nstr) == cudaSuccess) {
+            cudaMemcpy(p->d_dyn_init, init_map.data(), sizeof(uint32_t) * hp.nstr, cudaMemcpyHostToDevice);
+            const int64_t r = p->hf_index / hp.nb;  // static address of the Hartree-Fock string (rows keep the static order)
+            p->hf_index_dyn = r * hp.nb + int64_t(hp.dyn_col0[r]);
+            p->dyn = 1;
+        } else {
+            cudaGetLastError();
+        }
+    }
     cudaMemset(p->ticket, 0, sizeof(unsigned));
     cudaMemset(p->grad_ops, 0, sizeof(double) * (n_ops + 8));
     cudaEventRecord(p->rot_event, nullptr);
@@ -544,6 +570,9 @@ void tcc_plan_destroy(tcc_plan* p) {
     cudaFree(p->ws1);
     cudaFree(p->ws2);
     cudaFree(p->kb);
+    cudaFree(p->kb2);
+    cudaFree(p->dyn_f);
+    cudaFree(p->d_dyn_init);
     cudaFree(p->io1);
     cudaFree(p->io2);
     cudaFree(p->partials);
@@ -823,7 +852,10 @@ static void reverse_op(tcc_plan* p, int j, double theta, double* ket, double* br
 }
 
 // exp(theta_M G_M) ... exp(theta_1 G_1) applied to a storage-order vector (evolve_civector.py:165-177)
-static int forward_sweep(tcc_plan* p, const double* params, double* vec, cudaStream_t st) {
+// dyn_start: null = in place in the static order; otherwise the buffer (vec or p->dyn_f, chosen by the parity of the number
+// of batches so that the last batch writes vec) that holds the state in the first forward layout -- every batch then
+// reads one buffer and writes the other, the last one in the static order (dynamic column layout, plan.hpp)
+static int forward_sweep(tcc_plan* p, const double* params, double* vec, cudaStream_t st, double* dyn_start = nullptr) {
     HostPlan& hp = p->hp;
     if (p->mode == 1) {
         for (size_t j = 0; j < hp.ops.size(); ++j) rotate_op(p, int(j), params[hp.ops[j].param], vec, st);
@@ -832,10 +864,13 @@ static int forward_sweep(tcc_plan* p, const double* params, double* vec, cudaStr
         p->prof.mark(TCC_PROF_FWD_BATCH, st);
         const size_t nbt = p->dbatches.size();
         if (p->btimer.on) p->btimer.ensure(nbt);
+        double* cur = dyn_start ? dyn_start : vec;
+        double* other = dyn_start ? (dyn_start == vec ? p->dyn_f : vec) : nullptr;
         for (size_t b = 0; b < nbt; ++b) {
             BatchDevSet& db = p->dbatches[b];
             if (p->btimer.on) cudaEventRecord(p->btimer.ev[b], st);
-            launch_batch_forward(vec, hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
+            launch_batch_forward(cur, other, hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
+            if (other) std::swap(cur, other);
             p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * hp.N);
             p->launches += 1;
         }
@@ -873,6 +908,23 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
                 use_il = false;
             }
         }
+        // dynamic column layout: every batch reads one interleaved buffer (the first one in the static order) and writes the
+        // other in the order of the batch that follows; needs lean streams in every batch
+        bool dyn = use_il && p->dyn && nbt >= 2;
+        if (dyn)
+            for (auto& db : p->dbatches) dyn = dyn && db.rev.lean;
+        if (dyn && !p->kb2) {
+            double* kb2 = nullptr;
+            if (cudaMalloc(&kb2, sizeof(double) * 2 * size_t(hp.N)) == cudaSuccess) {
+                p->kb2 = kb2;
+                p->dev_bytes += int64_t(sizeof(double)) * 2 * hp.N;
+            } else {
+                cudaGetLastError();
+                dyn = false;
+            }
+        }
+        double* kb_cur = p->kb;
+        double* kb_other = dyn ? p->kb2 : nullptr;
         bool in_kb = false;
         for (int b = nbt - 1; b >= 0; --b) {
             BatchDevSet& db = p->dbatches[b];
@@ -883,8 +935,9 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
                     p->launches += 1;
                     in_kb = true;
                 }
-                launch_batch_reverse_il(p->kb, hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
-                                        SetStrides{0, 0, 0, 0}, st, &p->fan, p->rev_il_mode, p->persist_ctas);
+                launch_batch_reverse_il(kb_cur, kb_other, hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart,
+                                        p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
+                if (kb_other) std::swap(kb_cur, kb_other);
             } else {
                 if (in_kb) {
                     launch_deinterleave(p->kb, ket, bra, hp.N, st);
@@ -906,13 +959,33 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
 // state preparation into a storage-order buffer
 static int prepare_state(tcc_plan* p, const double* params, const double* init_ref_dev, double* vec, cudaStream_t st) {
     HostPlan& hp = p->hp;
+    // dynamic column layout: the state is prepared in the first forward layout, in the buffer from which an alternating
+    // sequence of batches ends in `vec`
+    bool dyn = p->dyn && p->mode != 1 && p->dbatches.size() >= 2 && init_ref_dev != vec;
+    if (dyn && !p->dyn_f) {
+        double* buf = nullptr;
+        if (cudaMalloc(&buf, sizeof(double) * size_t(hp.N)) == cudaSuccess) {
+            p->dyn_f = buf;
+            p->dev_bytes += int64_t(sizeof(double)) * hp.N;
+        } else {
+            cudaGetLastError();  // no memory for the second buffer: in place, static order
+            p->dyn = 0;
+            dyn = false;
+        }
+    }
+    double* start = dyn ? (p->dbatches.size() % 2 == 0 ? vec : p->dyn_f) : vec;
     if (init_ref_dev) {
-        to_storage(p, init_ref_dev, vec, st);
+        if (dyn) {
+            launch_permute(init_ref_dev, start, hp.na, hp.nb, p->d_int2ref, p->d_dyn_init, st);
+            p->launches += 1;
+        } else {
+            to_storage(p, init_ref_dev, vec, st);
+        }
     } else {
-        launch_set_unit(vec, hp.N, p->hf_index, 1, st);
+        launch_set_unit(start, hp.N, dyn ? p->hf_index_dyn : p->hf_index, 1, st);
         p->launches += 1;
     }
-    return forward_sweep(p, params, vec, st);
+    return forward_sweep(p, params, vec, st, dyn ? start : nullptr);
 }
 
 int tcc_apply_h(tcc_plan* p, const double* c_dev, double* sigma_dev, void* stream) {
@@ -1142,7 +1215,7 @@ int tcc_energy_and_grad_batch(tcc_plan* p, int n_sets, const double* params_host
         launch_set_unit(ws.ket, hp.N, p->hf_index, ns, st);
         p->launches += 1;
         for (auto& db : p->dbatches) {
-            launch_batch_forward(ws.ket, hp.nb, db.fwd, ws.rot_fwd, db.rects, p->batch_threads, ns,
+            launch_batch_forward(ws.ket, nullptr, hp.nb, db.fwd, ws.rot_fwd, db.rects, p->batch_threads, ns,
                                  SetStrides{hp.N, m, 0, 0}, st, &p->fan);
             p->launches += 1;
         }
@@ -1360,7 +1433,7 @@ int tcc_shard_forward(tcc_plan* p, int seg, double* vec_local_dev, void* stream)
     p->prof.mark(TCC_PROF_FWD_BATCH, st);
     for (int b = s.batch_lo; b < s.batch_hi; ++b) {
         BatchDevSet& db = p->dbatches[b];
-        launch_batch_forward(vec_local_dev, p->hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st,
+        launch_batch_forward(vec_local_dev, nullptr, p->hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st,
                              &p->fan);
         p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
         p->launches += 1;
@@ -1405,8 +1478,8 @@ int tcc_shard_reverse_interleaved(tcc_plan* p, int seg, double* kb_local_dev, vo
     p->prof.mark(TCC_PROF_REV_BATCH, st);
     for (int b = s.batch_hi - 1; b >= s.batch_lo; --b) {
         BatchDevSet& db = p->dbatches[b];
-        launch_batch_reverse_il(kb_local_dev, p->hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart, p->grad_ops, 1,
-                                SetStrides{0, 0, 0, 0}, st, &p->fan, p->rev_il_mode, p->persist_ctas);
+        launch_batch_reverse_il(kb_local_dev, nullptr, p->hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart,
+                                p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
         p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
         p->launches += 2;
     }

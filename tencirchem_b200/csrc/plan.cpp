@@ -788,7 +788,7 @@ void HostPlan::build_sigma_pass_links() {
     }
 }
 
-void HostPlan::finalize(int tile_elems, bool use_layout, int rank, int world, int lean_threads) {
+void HostPlan::finalize(int tile_elems, bool use_layout, int rank, int world, int lean_threads, bool use_dyn) {
     tile_elems = std::max(tile_elems, 64);
     shard_rank = rank;
     shard_world = world;
@@ -805,6 +805,76 @@ void HostPlan::finalize(int tile_elems, bool use_layout, int rank, int world, in
     for (size_t g = 0; g < groups.size(); ++g) active_sets(groups[g], tile_elems, &batches[g].sa, &batches[g].sb);
     choose_row_layouts();
     for (size_t g = 0; g < groups.size(); ++g) build_batch(groups[g], tile_elems, &batches[g], lean_threads);
+    if (use_dyn) build_dyn_layouts();
+}
+
+uint32_t HostPlan::rank_in_order(const std::vector<int>& order, uint32_t s) const {
+    int64_t r = 0;
+    int idx = 1;
+    for (int pos = 0; pos < n; ++pos)
+        if (s >> order[pos] & 1) {
+            r += binom[pos][idx];
+            ++idx;
+        }
+    return uint32_t(r);
+}
+
+// Per-batch column orders and the gather / scatter tables that go with them (plan.hpp, DYNAMIC COLUMN LAYOUT).
+void HostPlan::build_dyn_layouts() {
+    dyn_layout = false;
+    const size_t nbt = batches.size();
+    if (hcb || shard_world > 1 || nbt < 2 || nstr > 65535u * 65535u) return;
+    std::vector<int> stat(n);  // orbital at static position p
+    for (int o = 0; o < n; ++o) stat[bitpos[o]] = o;
+    // order of a batch with active set S next to a batch with active set T: [S & T][S & ~T][spectators], each part in
+    // static position order
+    auto order_of = [&](uint32_t S, uint32_t T) {
+        std::vector<int> o;
+        for (int pass = 0; pass < 3; ++pass)
+            for (int p = 0; p < n; ++p) {
+                const int orb = stat[p];
+                const bool in_s = S >> orb & 1, in_t = T >> orb & 1;
+                if ((in_s ? (in_t ? 0 : 1) : 2) == pass) o.push_back(orb);
+            }
+        return o;
+    };
+    // forward: batch k reads L^F_k = order_of(S_k, S_{k-1}); writes L^F_{k+1}; the last batch writes the static order.
+    // reverse: batch k reads L^R_k = order_of(S_k, S_{k+1}) (the last batch: static); writes L^R_{k-1}.
+    std::vector<std::vector<int>> lf(nbt + 1), lr(nbt);
+    for (size_t k = 0; k < nbt; ++k) {
+        const uint32_t sk = batches[k].B.S;
+        lf[k] = order_of(sk, k ? batches[k - 1].B.S : sk);
+        lr[k] = k + 1 < nbt ? order_of(sk, batches[k + 1].B.S) : stat;
+    }
+    lf[nbt] = stat;
+    auto tables = [&](const SideBatch& side, const std::vector<int>& order, ColTables* out) {
+        out->addr_sorted.resize(side.addr.size());
+        out->ord.resize(side.addr.size());
+        std::vector<uint32_t> a;
+        for (const PanelDesc& pd : side.panels) {
+            const int cnt = int(pd.G) * int(pd.c);
+            a.resize(cnt);
+            for (int i = 0; i < cnt; ++i) a[i] = rank_in_order(order, strings[side.addr[pd.off + i]]);
+            uint16_t* ord = out->ord.data() + pd.off;
+            std::iota(ord, ord + cnt, uint16_t(0));
+            std::sort(ord, ord + cnt, [&](uint16_t x, uint16_t y) { return a[x] < a[y]; });
+            for (int i = 0; i < cnt; ++i) out->addr_sorted[pd.off + i] = a[ord[i]];
+        }
+    };
+    for (size_t k = 0; k < nbt; ++k) {
+        Batch& b = batches[k];
+        if (b.B.addr.size() != size_t(nstr)) return;  // a beta side that does not list every column (never for whole-vector plans)
+        tables(b.B, lf[k], &b.dyn_fwd_in);
+        tables(b.B, lf[k + 1], &b.dyn_fwd_out);
+        tables(b.B, lr[k], &b.dyn_rev_in);
+        if (k > 0)
+            tables(b.B, lr[k - 1], &b.dyn_rev_out);
+        else
+            b.dyn_rev_out = b.dyn_rev_in;  // nothing reads what the last batch of the reverse sweep writes
+    }
+    dyn_col0.resize(size_t(nstr));
+    for (int64_t a = 0; a < nstr; ++a) dyn_col0[a] = rank_in_order(lf[0], strings[a]);
+    dyn_layout = true;
 }
 
 void HostPlan::build_links() {

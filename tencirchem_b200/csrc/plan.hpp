@@ -84,6 +84,13 @@ struct SideBatch {
     std::vector<int> ld_of_e;          // [m + 1] tile leading dimension when this side supplies the columns
 };
 
+// Column tables of a batch under a per-batch column order (dynamic column layout, see HostPlan::build_dyn_layouts):
+// per panel, like SideBatch::addr_sorted / ::ord, but with the beta strings addressed in another bit order
+struct ColTables {
+    std::vector<uint32_t> addr_sorted;  // [nstr] per panel: column addresses, ascending
+    std::vector<uint16_t> ord;          // [nstr] per panel: the local index of each of them
+};
+
 struct BatchOp {
     int32_t op_index;
     int32_t h_a, h_b;  // local hop ids (-1 = identity)
@@ -112,6 +119,8 @@ struct Batch {
     int ld_fixed = 0;                  // tile leading dimension when the beta side has no active orbitals
     uint32_t sa = 0, sb = 0;           // padded active sets
     int layout = 0;                    // row distribution the batch runs in (sharded plans)
+    // dynamic column layout: the tables the forward / reverse sweep gathers from and scatters to (empty = static order)
+    ColTables dyn_fwd_in, dyn_fwd_out, dyn_rev_in, dyn_rev_out;
 };
 
 // Row distribution of a sharded plan: alpha string a lives on rank owner[a] (the occupation pattern of the
@@ -162,13 +171,27 @@ struct HostPlan {
     }
     int n_params = 0;
     std::string error;
+    // DYNAMIC COLUMN LAYOUT (whole-vector plans).  In the static storage order a beta class of a batch is contiguous
+    // only when the active beta orbitals of the batch happen to sit in the lowest bit positions; over a UCCSD sweep the
+    // mean run of consecutive columns in a tile is below 3 elements, and the tile gather / scatter is bound by the
+    // number of distinct 128-byte lines per warp instruction, not by bytes (profiles/r02_reverse_kernel_breakdown.md).
+    // With the dynamic layout every batch k READS the CI matrix with its columns in an order L_k whose lowest bit
+    // positions are the active beta orbitals of the batch (every beta class is one contiguous block of columns) and
+    // WRITES it in the order of the batch that follows in the sweep (out of place, two buffers); the orbitals shared
+    // with that batch come first in its order, so a class is written in runs of C(|shared|, .) columns.  The forward
+    // sweep starts from L^F_0 (dyn_col0: static column address -> address in L^F_0) and ends in the static order; the
+    // reverse sweep starts from the static order.  Rows (alpha strings) keep the static order.
+    bool dyn_layout = false;
+    std::vector<uint32_t> dyn_col0;  // [nstr] static column address -> column address in the first forward layout
+    void build_dyn_layouts();
+    uint32_t rank_in_order(const std::vector<int>& order, uint32_t s) const;  // order[pos] = orbital at bit position pos
 
     int init(int n_qubits, int n_elec, int hcb);
     // validation + masks + sign; no tables (strings may not exist yet)
     int parse_op(const int32_t* idx, int len, int param, OpDesc* op);
     // groups ops into batches (orbital sets only), picks the storage order, builds strings, hop tables
     // and batch descriptors.  tile_elems = max determinants per on-chip tile.
-    void finalize(int tile_elems, bool use_layout, int rank = 0, int world = 1, int lean_threads = 256);
+    void finalize(int tile_elems, bool use_layout, int rank = 0, int world = 1, int lean_threads = 256, bool use_dyn = false);
     void attach_hops(OpDesc* op);
 
     uint32_t permute_bits(uint32_t s) const;

@@ -306,6 +306,45 @@ def test_small_tiles_many_batches(tile_elems, threads, monkeypatch):
     clear_cache()
 
 
+@pytest.mark.parametrize("tile_elems", [64, 400, 1500])
+def test_dynamic_column_layout_against_static_and_oracle(tile_elems, monkeypatch):
+    """Dynamic column layout (every batch gathers its tiles from contiguous columns and scatters in the order of the
+    next batch, out of place; plan.hpp) against the in-place static order and the oracle: state, energy, gradient, with
+    and without an init_state, odd and even numbers of batches."""
+    monkeypatch.setenv("TCC_B200_TILE_ELEMS", str(tile_elems))
+    seen_batches = set()
+    for kind, no, nv in [("uccsd", 4, 4), ("uccsd", 3, 4), ("uccsd", 2, 4), ("kupccgsd", 3, 3)]:
+        ucc, int1e, int2e = _build(kind, no, nv)
+        params = _params(ucc.n_params)
+        rng = np.random.default_rng(7)
+        init = rng.standard_normal(ucc.civector_size)
+        init /= np.linalg.norm(init)
+        res = {}
+        for dyn in ("1", "0"):
+            monkeypatch.setenv("TCC_B200_DYN_LAYOUT", dyn)
+            clear_cache()
+            plan = Plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids)
+            plan.set_hamiltonian(int1e, int2e)
+            seen_batches.add(plan.n_batches)
+            e, g = plan.energy_and_grad(params)
+            c = plan.civector(params)
+            ci = plan.civector(params, init)
+            ei, gi = plan.energy_and_grad(params, init)
+            res[dyn] = (e, g, c, ci, ei, gi)
+        for x, y in zip(res["1"], res["0"]):
+            assert np.abs(np.asarray(x) - np.asarray(y)).max() < 1e-13
+        h = O.get_h_from_integral(int1e, int2e, ucc.n_elec, False)
+        e_ref, g_ref = O.get_energy_and_grad(params, h, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False)
+        c_ref = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False)
+        ci_ref = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False, init_state=init)
+        e, g, c, ci, ei, gi = res["1"]
+        assert abs(e - e_ref) < E_TOL and np.abs(g - g_ref).max() < G_TOL
+        assert np.abs(c - c_ref).max() < C_TOL and np.abs(ci - ci_ref).max() < C_TOL
+        O.clear_cache()
+    assert any(b > 1 for b in seen_batches)
+    clear_cache()
+
+
 def test_batch_schedule_is_a_valid_reordering():
     """Every excitation appears exactly once, and two excitations whose relative order changed act on disjoint
     spin-orbitals (so their generators commute and the product of factors is unchanged)."""

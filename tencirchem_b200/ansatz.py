@@ -303,6 +303,15 @@ class UCC:
         """ucc.py:1033-1038."""
         return self.energy()
 
+    @property
+    def e_fci(self) -> float:
+        """FCI energy of the active space (ucc.py:284-300 takes it from PySCF): Lanczos on the engine's H.c, cached."""
+        if getattr(self, "_e_fci", None) is None:
+            from .fci import fci_energy
+
+            self._e_fci = fci_energy(self)
+        return self._e_fci
+
     def _minimize_options(self) -> dict:
         """ucc.py:355-360: the reference's strict L-BFGS-B defaults (ftol = 10 eps, gtol = 100 eps of float64)
         unless ``scipy_minimize_options`` is set."""
@@ -338,25 +347,84 @@ class UCC:
         return opt_res["e"]
 
 
-class UCCSD(UCC):
-    """uccsd.py:20-185 without amplitude screening (``pick_ex2=False, sort_ex2=False``)."""
+DISCARD_EPS = 1e-12  # tencirchem/constants.py: two-body excitations with a smaller initial amplitude are dropped
 
-    def __init__(self, int1e, int2e, n_elec, e_core=0.0, **kwargs):
+
+def _spin_t2(t2, i, j, a, b, kind):
+    """Element of ``spatial2spin(t2)`` (PySCF cc.addons, even = alpha, odd = beta) that ucc.py:938-1031 reads for an
+    excitation of `kind`: "same" -> t2s[2i, 2j, 2a, 2b] (antisymmetrised), "ab" -> t2s[2i, 2j+1, 2a, 2b+1]."""
+    if kind == "same":
+        return t2[i, j, a, b] - t2[i, j, b, a]
+    return t2[i, j, a, b]
+
+
+class UCCSD(UCC):
+    """uccsd.py:20-185.  Without amplitudes (``t2=None``, the default of :meth:`from_integral`, whose integrals need
+    not come from a Hartree-Fock calculation) every excitation is kept in generator order with a zero initial guess.
+    With MP2 amplitudes (``t2`` in PySCF's spatial ``[no, no, nv, nv]`` layout, e.g. from
+    :func:`tencirchem_b200.hchain.mp2_t2`; ``init_method="mp2"`` in the reference) the two-body excitations are
+    screened (``pick_ex2``: ``|t2| < epsilon`` dropped) and sorted by ``|t2|`` (``sort_ex2``) exactly as
+    ``UCCSD.pick_and_sort`` does (uccsd.py:159-178), and the amplitudes are the initial guess."""
+
+    def __init__(self, int1e, int2e, n_elec, e_core=0.0, t1=None, t2=None, pick_ex2: bool = True, sort_ex2: bool = True,
+                 epsilon: float = DISCARD_EPS, **kwargs):
         super().__init__(int1e, int2e, n_elec, e_core, hcb=False, **kwargs)
+        self.t1 = None if t1 is None else np.asarray(t1, dtype=np.float64)
+        self.t2 = None if t2 is None else np.asarray(t2, dtype=np.float64)
+        if self.t2 is not None and self.t2.shape != (self.no, self.no, self.nv, self.nv):
+            raise ValueError(f"t2 must have the spatial shape {(self.no, self.no, self.nv, self.nv)}")
+        self.pick_ex2 = bool(pick_ex2) and self.t2 is not None
+        self.sort_ex2 = bool(sort_ex2) and self.t2 is not None
+        self.t2_discard_eps = float(epsilon)
         self.ex_ops, self.param_ids, self.init_guess = self.get_ex_ops()
 
     def get_ex1_ops(self):
+        """ucc.py:889-936; initial guess = t1[i, a] (zeros without CCSD amplitudes)."""
         ops, ids = _flatten(_uccsd_singles(self.no, self.nv))
-        return ops, ids, [0.0] * (max(ids) + 1 if ids else 0)
+        guess = [0.0] * (max(ids) + 1 if ids else 0)
+        if self.t1 is not None:
+            guess = [float(self.t1[i, a]) for i in range(self.no) for a in range(self.nv)]
+        return ops, ids, guess
 
     def get_ex2_ops(self):
+        """ucc.py:938-1031; the initial guess of each parameter is the spin-orbital amplitude the reference reads."""
         ops, ids = _flatten(_uccsd_doubles(self.no, self.nv))
-        return ops, ids, [0.0] * (max(ids) + 1 if ids else 0)
+        n_par = max(ids) + 1 if ids else 0
+        if self.t2 is None:
+            return ops, ids, [0.0] * n_par
+        no, nv, t2 = self.no, self.nv, self.t2
+        guess = []
+        for i in range(no):
+            for j in range(i):
+                for a in range(nv):
+                    for b in range(a):
+                        guess.append(float(_spin_t2(t2, i, j, a, b, "same")))
+        for i in range(no):
+            for j in range(i + 1):
+                for a in range(nv):
+                    for b in range(a + 1):
+                        guess.append(float(_spin_t2(t2, i, j, a, b, "ab")))
+                        if not (i == j and a == b) and i != j and a != b:
+                            guess.append(float(_spin_t2(t2, i, j, b, a, "ab")))
+        assert len(guess) == n_par
+        return ops, ids, guess
+
+    def pick_and_sort(self, ex_ops, param_ids, init_guess, do_pick=True, do_sort=True):
+        """uccsd.py:159-178 (stable sort by decreasing |amplitude|, drop below epsilon, renumber the parameters)."""
+        pairs = list(zip(ex_ops, param_ids))
+        if do_sort:
+            pairs = sorted(pairs, key=lambda x: -abs(init_guess[x[1]]))
+        kept = [(op, pid) for op, pid in pairs if not (do_pick and abs(init_guess[pid]) < self.t2_discard_eps)]
+        unique_ids = sorted({pid for _, pid in kept})
+        mapping = {old: new for new, old in enumerate(unique_ids)}
+        return [op for op, _ in kept], [mapping[pid] for _, pid in kept], [init_guess[i] for i in unique_ids]
 
     def get_ex_ops(self):
         """uccsd.py:107-157."""
         o1, p1, g1 = self.get_ex1_ops()
         o2, p2, g2 = self.get_ex2_ops()
+        if self.pick_ex2 or self.sort_ex2:
+            o2, p2, g2 = self.pick_and_sort(o2, p2, g2, self.pick_ex2, self.sort_ex2)
         off = max(p1) + 1 if p1 else 0
         return o1 + o2, p1 + [p + off for p in p2], g1 + g2
 

@@ -711,6 +711,300 @@ lean_batch_kernel(double* __restrict__ v0, double* __restrict__ v1, double* __re
     }
 }
 
+// ================================================================================================================
+// Persistent lean kernel.  Same tiles, streams and arithmetic as lean_batch_kernel; what changes is the life of a CTA.
+// ncu on the one-tile-per-CTA kernels (profiles/r02_batch_kernels_16o_ncu.txt) shows that a tile spends more time
+// waiting than moving data: the CTA start-up is a chain of dependent L2 round trips (panel descriptors -> row / column
+// addresses -> tile gather; excitation records -> angles; stream offsets -> first stream entries), none of which can be
+// hidden with two CTAs per SM, and every tile pays the CTA launch itself.  Here a CTA stays resident and takes tiles
+// from a ticket counter; while the gather of tile k is in flight it resolves EVERYTHING tile k+1 needs except the
+// data (descriptors, addresses, records, masks -- double-buffered in a few KB of shared memory), and the ticket of
+// tile k+2.  Per tile the critical path is: gather -> excitations -> scatter.
+// NV == 1: forward sweep; NV == 3: reverse sweep on interleaved (ket, bra) elements.  One parameter set, static column
+// order, tiles of at most 32 * BK_COLCH columns (the launchers fall back to lean_batch_kernel otherwise).
+// ================================================================================================================
+struct PersistTile {  // what the op loop of a tile needs, resolved one tile ahead
+    PanelDesc pa, pb;
+    int tile_id;  // index into the per-tile gradient partials; -1 = no tile
+    int pad[3];
+};
+
+template <int NV>
+__global__ void __launch_bounds__(BK_THREADS, NV == 1 ? LK_FWD_MINB : 2)
+lean_persist_kernel(double* __restrict__ v0, int64_t nb, BatchDev bd, const double2* __restrict__ rot, double* __restrict__ partials,
+                    int n_tiles, TileRect rect, unsigned* __restrict__ ctl, int max_rows, int max_cols) {
+    constexpr int NVEC = NV == 1 ? 1 : 2;
+    constexpr int ELW = NV == 3 ? 16 : 8;
+    constexpr int ESH = NV == 3 ? 4 : 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const int nops = bd.nops;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rect_tiles = rect.pa_cnt * rect.pb_cnt;
+    // shared memory: tile | records [2][nops] | warp partials [nops][nwarps] | meta [2][nops] | masks [2][nops] |
+    // row addresses [2][max_rows] | column addresses [2][max_cols] | local columns [2][max_cols] | tile records [2] | tickets [2]
+    const size_t tile_bytes = (size_t(max_rows) * (size_t(max_cols) | 1) * ELW + 15) & ~size_t(15);
+    unsigned char* t0 = smem_raw;
+    double2* recs = reinterpret_cast<double2*>(t0 + tile_bytes);
+    double* wpart = reinterpret_cast<double*>(recs + 2 * nops);
+    uint2* metas = reinterpret_cast<uint2*>(wpart + (NVEC == 2 ? size_t(nops) * nwarps : 0));
+    uint32_t* smasks = reinterpret_cast<uint32_t*>(metas + 2 * nops);
+    uint32_t* row_addr = smasks + 2 * nops;
+    uint32_t* col_g = row_addr + 2 * max_rows;
+    PersistTile* tiles = reinterpret_cast<PersistTile*>((reinterpret_cast<uintptr_t>(col_g + 2 * max_cols) + 15) & ~uintptr_t(15));
+    int* tickets = reinterpret_cast<int*>(tiles + 2);
+    uint16_t* col_l = reinterpret_cast<uint16_t*>(tickets + 4);
+
+    // resolves tile `lin` of the rectangle into buffer `buf`: two rounds of independent global loads
+    auto resolve = [&](int lin, int buf) {
+        if (lin >= rect_tiles) {
+            if (tid == 0) tiles[buf].tile_id = -1;
+            return;
+        }
+        const int pa_loc = lin / rect.pb_cnt;
+        const int pa_id = rect.pa_lo + pa_loc;
+        const int pb_id = rect.pb_lo + (lin - pa_loc * rect.pb_cnt);
+        const PanelDesc pa = bd.A.panels[pa_id];
+        const PanelDesc pb = bd.B.panels[pb_id];
+        BatchOp op0;
+        if (tid < nops) op0 = bd.ops[tid];  // in flight together with the descriptors
+        const int nR = int(pa.G) * int(pa.c), nC = int(pb.G) * int(pb.c);
+        for (int i = tid; i < nR; i += nthreads) row_addr[buf * max_rows + i] = __ldg(bd.A.addr + pa.off + i);
+        for (int i = tid; i < nC; i += nthreads) {
+            col_g[buf * max_cols + i] = __ldg(bd.B.addr_sorted + pb.off + i);
+            col_l[buf * max_cols + i] = __ldg(bd.B.ord + pb.off + i);
+        }
+        const bool multi = max(1, int(pa.Gn)) * max(1, int(pb.Gn)) > 1;
+        for (int t = tid; t < nops; t += nthreads) {
+            const BatchOp op = t == tid ? op0 : bd.ops[t];
+            const int fwd_pos = bd.reversed ? nops - 1 - t : t;
+            const int* si = bd.stream_index + ((size_t(fwd_pos) * (bd.A.m + 1) + int(pa.e)) * (bd.B.m + 1) + int(pb.e)) * 2;
+            const int si0 = __ldg(si), si1 = __ldg(si + 1);
+            const double2 cs = __ldg(rot + op.op_index);
+            uint32_t smask = 0;
+            if (op.h_a >= 0)
+                for (int g = 0; g < int(pa.G); ++g) smask |= (uint32_t(__popc(__ldg(bd.A.sigma + pa.class_off + g) & op.zspec_a)) & 1u) << g;
+            if (op.h_b >= 0)
+                for (int g = 0; g < int(pb.G); ++g) smask |= (uint32_t(__popc(__ldg(bd.B.sigma + pb.class_off + g) & op.zspec_b)) & 1u) << (16 + g);
+            const bool fold = !multi && (((smask ^ (smask >> 16)) & 1u) != 0);
+            recs[buf * nops + t] = make_double2(cs.x, fold ? -cs.y : cs.y);
+            metas[buf * nops + t] = make_uint2(uint32_t(si0), uint32_t(si1));
+            smasks[buf * nops + t] = smask;
+        }
+        if (tid == 0) {
+            tiles[buf].pa = pa;
+            tiles[buf].pb = pb;
+            tiles[buf].tile_id = pa_id * bd.B.n_panels + pb_id;
+        }
+    };
+
+    if (tid == 0) {
+        tickets[0] = int(atomicAdd(ctl, 1u));
+        tickets[1] = int(atomicAdd(ctl, 1u));
+    }
+    __syncthreads();
+    int lin_next = tickets[1];
+    resolve(tickets[0], 0);
+    __syncthreads();
+
+    const uint32_t* __restrict__ stream = NV == 3 ? bd.stream16 : bd.stream8;
+    const uint32_t t0_s = uint32_t(__cvta_generic_to_shared(t0));
+    for (int cur = 0;; cur ^= 1) {
+        const int tile_id = tiles[cur].tile_id;
+        if (tile_id < 0) break;
+        const PanelDesc pa = tiles[cur].pa, pb = tiles[cur].pb;
+        const int nR = int(pa.G) * int(pa.c), nC = int(pb.G) * int(pb.c);
+        const int ld = int(pb.ld);
+        const int Gan = max(1, int(pa.Gn)), Gbn = max(1, int(pb.Gn));
+        const int nsub = Gan * Gbn;
+        const int tps = nthreads / nsub;
+        const int sub = tid / tps;
+        const int ga = sub / Gbn, gb = sub - ga * Gbn;
+        const bool active = sub < nsub && ga < int(pa.G) && gb < int(pb.G);
+        const int lid = tid - sub * tps;
+        const int sbase = active ? ga * int(pa.c) * ld + gb * int(pb.c) : 0;
+        const int sshift_a = ga, sshift_b = 16 + gb;
+        const bool multi = nsub > 1;
+        const uint32_t* ra_s = row_addr + cur * max_rows;
+
+        // ---- gather (asynchronous copies); the lane's columns stay in registers for the scatter
+        int64_t colg[BK_COLCH];
+        int lcs[BK_COLCH];
+#pragma unroll
+        for (int j = 0; j < BK_COLCH; ++j) {
+            const int t = lane + 32 * j;
+            colg[j] = 0;
+            lcs[j] = -1;
+            if (t < nC) {
+                colg[j] = col_g[cur * max_cols + t];
+                lcs[j] = col_l[cur * max_cols + t];
+            }
+        }
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
+            const int64_t ra = int64_t(ra_s[lr]) * nb;
+#pragma unroll
+            for (int j = 0; j < BK_COLCH; ++j)
+                if (lcs[j] >= 0) {
+                    if (NV == 3)
+                        cp_async16(t0 + (size_t(lr) * ld + lcs[j]) * 16, v0 + (ra + colg[j]) * 2);
+                    else
+                        cp_async8(reinterpret_cast<double*>(t0) + lr * ld + lcs[j], v0 + ra + colg[j]);
+                }
+        }
+        // ---- while the gather is in flight: first stream entries of this tile, everything of the next tile, next ticket
+        const uint32_t* __restrict__ sp = stream + lid;
+        const uint32_t sh0 = t0_s + (uint32_t(sbase) << ESH);
+        const uint32_t rec_s = uint32_t(__cvta_generic_to_shared(recs + cur * nops));
+        const uint32_t meta_s = uint32_t(__cvta_generic_to_shared(metas + cur * nops));
+        const uint32_t mask_s = uint32_t(__cvta_generic_to_shared(smasks + cur * nops));
+        uint32_t cur0[LK_DEPTH], cur1[LK_DEPTH], nxt0[LK_DEPTH], nxt1[LK_DEPTH];
+        double accs[LK_DEPTH];
+        auto fetch = [&](int tbase, uint32_t* e0, uint32_t* e1) {
+#pragma unroll
+            for (int j = 0; j < LK_DEPTH; ++j) {
+                const int t = tbase + j;
+                e0[j] = 0;
+                e1[j] = 0;
+                if (t < nops && active) {
+                    const uint2 m = lds64u(meta_s + t * 8);
+                    if (m.y > 0) e0[j] = __ldg(sp + m.x);
+                    if (m.y > 1) e1[j] = __ldg(sp + m.x + tps);
+                }
+            }
+        };
+        auto pair = [&](uint32_t e, double cs, double sn, uint32_t sflip, double& acc) {
+            const uint32_t flip = ((e << 1) & 0x80000000u) ^ sflip;
+            const double p = flip_sign(sn, flip);
+            if (NV == 3) {
+                const uint32_t o1 = (e & 0x7fffu) << 4, o2 = (e >> 11) & 0x7fff0u;
+                const double2 a = lds128(sh0 + o1), b = lds128(sh0 + o2);
+                acc = fma(flip_sign(a.y, flip), b.x, acc);
+                acc = fma(-flip_sign(b.y, flip), a.x, acc);
+                sts128(sh0 + o1, cs * a.x + p * b.x, cs * a.y + p * b.y);
+                sts128(sh0 + o2, cs * b.x - p * a.x, cs * b.y - p * a.y);
+            } else {
+                const uint32_t o1 = (e & 0x7fffu) << 3, o2 = (e >> 12) & 0x3fff8u;
+                const double x = lds64(sh0 + o1), y = lds64(sh0 + o2);
+                sts64(sh0 + o1, cs * x + p * y);
+                sts64(sh0 + o2, cs * y - p * x);
+            }
+        };
+        fetch(0, cur0, cur1);
+        int lin_after = 0x7fffffff;
+        if (tid == 0 && lin_next < rect_tiles) lin_after = int(atomicAdd(ctl, 1u));
+        resolve(lin_next, cur ^ 1);
+        if (tid == 0) tickets[2 + cur] = lin_after;
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        __syncthreads();
+        lin_next = tickets[2 + cur];
+
+        // ---- the excitations of the batch, in order
+#ifdef TCC_DEBUG_SKIP_OPS
+        const int nops_loop = 0;
+#else
+        const int nops_loop = nops;
+#endif
+        for (int tb = 0; tb < nops_loop; tb += LK_DEPTH) {
+            fetch(tb + LK_DEPTH, nxt0, nxt1);
+#pragma unroll
+            for (int j = 0; j < LK_DEPTH; ++j) {
+                const int t = tb + j;
+                accs[j] = 0.0;
+                if (t < nops) {
+                    const uint32_t e0 = cur0[j], e1 = cur1[j];
+                    if (e0 & LK_VALID) {
+                        const double2 r = lds128(rec_s + t * 16);
+                        const double sn = r.y;
+                        uint32_t sflip = 0;
+                        if (multi) {
+                            const uint32_t sm = lds32u(mask_s + t * 4);
+                            sflip = ((sm >> sshift_a) ^ (sm >> sshift_b)) << 31;
+                        }
+                        double acc = 0.0;
+                        pair(e0, r.x, sn, sflip, acc);
+                        if (e1 & LK_VALID) {
+                            pair(e1, r.x, sn, sflip, acc);
+                            const uint2 m = lds64u(meta_s + t * 8);
+                            for (uint32_t s_ = 2; s_ < m.y; ++s_) {
+                                const uint32_t e = __ldg(sp + m.x + s_ * tps);
+                                if (e & LK_VALID) pair(e, r.x, sn, sflip, acc);
+                            }
+                        }
+                        accs[j] = acc;
+                    }
+                    __syncthreads();
+                }
+            }
+            if (NVEC == 2) {
+                static_assert(LK_DEPTH == 4, "the reduction below is written for groups of four");
+                const bool hi16 = lane & 16, hi8 = lane & 8;
+                const double s0 = hi16 ? accs[0] : accs[2], s1 = hi16 ? accs[1] : accs[3];
+                double k0 = (hi16 ? accs[2] : accs[0]) + __shfl_xor_sync(0xffffffffu, s0, 16);
+                double k1 = (hi16 ? accs[3] : accs[1]) + __shfl_xor_sync(0xffffffffu, s1, 16);
+                double k = (hi8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+                k += __shfl_xor_sync(0xffffffffu, k, 4);
+                k += __shfl_xor_sync(0xffffffffu, k, 2);
+                k += __shfl_xor_sync(0xffffffffu, k, 1);
+                if ((lane & 7) == 0) {
+                    const int j = ((lane >> 4) << 1) | ((lane >> 3) & 1);
+                    if (tb + j < nops) wpart[(tb + j) * nwarps + warp] = k;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < LK_DEPTH; ++j) {
+                cur0[j] = nxt0[j];
+                cur1[j] = nxt1[j];
+            }
+        }
+
+        // ---- scatter the tile back
+        for (int lr = warp; lr < TCC_MEM_ROWS(nR); lr += nwarps) {
+            const int64_t ra = int64_t(ra_s[lr]) * nb;
+#pragma unroll
+            for (int j = 0; j < BK_COLCH; ++j)
+                if (lcs[j] >= 0) {
+                    if (NV == 3)
+                        reinterpret_cast<double2*>(v0)[ra + colg[j]] = reinterpret_cast<const double2*>(t0)[lr * ld + lcs[j]];
+                    else
+                        v0[ra + colg[j]] = reinterpret_cast<const double*>(t0)[lr * ld + lcs[j]];
+                }
+        }
+        __syncthreads();  // the tile buffer is free; the warp partials are complete
+        if (NVEC == 2) {
+            for (int t = tid; t < nops; t += nthreads) {
+                double s = 0.0;
+                for (int w = 0; w < nwarps; ++w) s += wpart[t * nwarps + w];
+                const uint32_t sm = smasks[cur * nops + t];
+                if (!multi && (((sm ^ (sm >> 16)) & 1u) != 0)) s = -s;
+                partials[int64_t(t) * n_tiles + tile_id] = s;
+            }
+            __syncthreads();  // before the next tile overwrites the partials or this tile's masks
+        }
+    }
+    // the last CTA to leave resets the ticket counter for the next launch that uses this slot
+    if (tid == 0) {
+        __threadfence();
+        const unsigned d = atomicAdd(ctl + 1, 1u);
+        if (d == gridDim.x - 1) {
+            ctl[0] = 0;
+            ctl[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+size_t lean_persist_smem_bytes(int max_rows, int max_cols, int nops, int nv) {
+    const size_t elw = nv == 3 ? 16 : 8;
+    size_t bytes = (size_t(max_rows) * (size_t(max_cols) | 1) * elw + 15) & ~size_t(15);
+    bytes += 2 * size_t(nops) * 16;                                    // records
+    if (nv >= 2) bytes += size_t(nops) * BK_WARPS * sizeof(double);   // warp partials
+    bytes += 2 * size_t(nops) * 8 + 2 * size_t(nops) * 4;              // meta, masks
+    bytes += 2 * size_t(max_rows) * 4 + 2 * size_t(max_cols) * 4;      // row / column addresses
+    bytes += 16 + 2 * sizeof(PersistTile) + 16;                        // alignment, tile records, tickets
+    bytes += 2 * size_t(max_cols) * 2;                                 // local columns
+    return bytes + 16;
+}
+
 size_t lean_smem_bytes(int max_rows, int max_cols, int nops, int nv) {
     const size_t ld = size_t(max_cols) | 1;
     const size_t elw = nv == 3 ? 16 : 8;
@@ -778,12 +1072,29 @@ size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv) {
     return bytes + 16;
 }
 
+// shared memory and resident CTAs per SM of the persistent kernel for tiles up to max_rows x max_cols (0 CTAs: not usable)
+void persist_config(int nv, int threads, int max_rows, int max_cols, int nops, size_t* smem, int* ctas_per_sm) {
+    *smem = lean_persist_smem_bytes(max_rows, max_cols, nops, nv);
+    *ctas_per_sm = 0;
+    if (max_cols > 32 * BK_COLCH || *smem > 232448) return;
+    int n = 0;
+    cudaError_t e = nv == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lean_persist_kernel<1>, threads, *smem)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lean_persist_kernel<3>, threads, *smem);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    *ctas_per_sm = n;
+}
+
 cudaError_t batch_kernels_configure() {
     cudaError_t e = cudaFuncSetAttribute(batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lean_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lean_batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lean_batch_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lean_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lean_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
@@ -841,10 +1152,16 @@ static void fan_out(const std::vector<TileRect>& rects, cudaStream_t st, StreamF
 
 // v_out: null = in place (static column order); otherwise out of place with the dynamic column layout (BatchDev::B.dyn_*)
 void launch_batch_forward(double* v, double* v_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan) {
+                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan, unsigned* ctl, int sms) {
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
         if (grid.x == 0) return;  // a rank of a sharded plan may own no class of this batch
+        const size_t ri = size_t(&r - rects.data());
+        if (bd.lean && ctl && !v_out && n_sets == 1 && r.ctas_p_fwd > 0 && ri < 16) {
+            const unsigned ctas = std::min(grid.x, unsigned(r.ctas_p_fwd) * unsigned(sms));
+            lean_persist_kernel<1><<<ctas, threads, r.smem_p_fwd, s>>>(v, nb, bd, rot, nullptr, 0, r, ctl + 2 * ri, r.max_rows, r.max_cols);
+            return;
+        }
         if (bd.lean)
             lean_batch_kernel<1><<<grid, threads, r.smem_fwd, s>>>(v, nullptr, v_out, nb, bd, rot, nullptr, 0, ss, r);
         else
@@ -871,11 +1188,18 @@ void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& 
 // static column order; otherwise the batch reads kb with its columns in the batch's own order and writes kb_out in the
 // order of the next batch of the sweep (BatchDev::B.dyn_*, dynamic column layout)
 void launch_batch_reverse_il(double* kb, double* kb_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan) {
+                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan,
+                             unsigned* ctl, int sms) {
     const int n_tiles = bd.B.n_panels * bd.A.n_panels;
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         const unsigned tiles = unsigned(r.pa_cnt) * unsigned(r.pb_cnt);
         if (tiles == 0) return;
+        const size_t ri = size_t(&r - rects.data());
+        if (ctl && !kb_out && n_sets == 1 && r.ctas_p_rev > 0 && ri < 16) {
+            const unsigned ctas = std::min(tiles, unsigned(r.ctas_p_rev) * unsigned(sms));
+            lean_persist_kernel<3><<<ctas, threads, r.smem_p_rev, s>>>(kb, nb, bd, rot, partials, n_tiles, r, ctl + 32 + 2 * ri, r.max_rows, r.max_cols);
+            return;
+        }
         lean_batch_kernel<3><<<dim3(tiles, unsigned(n_sets), 1), threads, r.smem_il, s>>>(kb, nullptr, kb_out, nb, bd, rot, partials, n_tiles, ss, r);
     });
     batch_grad_reduce_kernel<<<dim3(bd.nops, unsigned(n_sets), 1), 256, 0, st>>>(partials, n_tiles, bd.ops, grad_ops, ss);

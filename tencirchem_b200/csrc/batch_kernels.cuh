@@ -55,6 +55,9 @@ struct TileRect {
     size_t smem_fwd, smem_rev;
     size_t smem_il;   // reverse sweep on interleaved (ket, bra) elements (lean_batch_kernel<3>)
     int max_rows, max_cols;
+    // persistent kernel (lean_persist_kernel): shared memory and resident CTAs per SM; 0 CTAs = not usable for this rectangle
+    size_t smem_p_fwd = 0, smem_p_rev = 0;
+    int ctas_p_fwd = 0, ctas_p_rev = 0;
 };
 
 // Auxiliary streams for the rectangle launches of one batch: the rectangles are independent sets of tiles, so they
@@ -70,12 +73,15 @@ struct StreamFan {
 cudaError_t batch_kernels_configure();
 size_t batch_smem_bytes(int max_rows, int max_cols, int nops, int nv);
 size_t lean_smem_bytes(int max_rows, int max_cols, int nops, int nv);
+size_t lean_persist_smem_bytes(int max_rows, int max_cols, int nops, int nv);
+void persist_config(int nv, int threads, int max_rows, int max_cols, int nops, size_t* smem, int* ctas_per_sm);
 void launch_batch_reverse_il(double* kb, double* kb_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan);
+                             int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan,
+                             unsigned* ctl = nullptr, int sms = 148);
 void launch_interleave(const double* a, const double* b, double* out, int64_t n, cudaStream_t st);
 void launch_deinterleave(const double* in, double* a, double* b, int64_t n, cudaStream_t st);
 void launch_batch_forward(double* v, double* v_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan);
+                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan, unsigned* ctl = nullptr, int sms = 148);
 void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot,
                           const std::vector<TileRect>& rects, int threads, double* partials, double* grad_ops, int n_sets,
                           SetStrides ss, cudaStream_t st, StreamFan* fan);

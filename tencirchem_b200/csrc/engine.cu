@@ -145,6 +145,11 @@ struct tcc_plan {
     int lean = 1;           // lean per-thread streams for two-sided batches (TCC_B200_LEAN=0: the plain pair lists)
     int lean_fwd = 0;       // forward sweep on the lean kernel too (TCC_B200_LEAN_FWD=1); measured slower than batch_kernel<1>
     int rev_interleave = 1; // reverse sweep on interleaved (ket, bra) elements (TCC_B200_REV_IL=0: two vectors)
+    int sigma_overlap = 0;  // H.c on two streams (TCC_B200_SIGMA_OVERLAP=1), see apply_h_sets
+    int persist_rev = 1;    // reverse sweep on the persistent kernel (lean_persist_kernel<3>; TCC_B200_PERSIST=0: one tile per CTA)
+    int persist_fwd = 0;    // forward sweep on lean_persist_kernel<1> (TCC_B200_PERSIST_FWD=1; needs the lean forward streams)
+    unsigned* persist_ctl = nullptr;  // ticket counters of the persistent launches [2][16][2], self-resetting
+    int sms = 148;
     int dyn = 0;            // dynamic column layout (plan.hpp, TCC_B200_DYN_LAYOUT=1; off by default: measured no faster and it takes
                             // three more vectors): out-of-place sweeps, every batch gathers contiguous columns
     double* dyn_f = nullptr;   // second buffer of the forward sweep [N]
@@ -243,6 +248,7 @@ static int upload_batches(tcc_plan* p) {
     HostPlan& hp = p->hp;
     p->dbatches.resize(hp.batches.size());
     size_t max_part = 1;
+    CUDA_TRY(batch_kernels_configure());  // before the occupancy queries of the persistent kernel below
     for (size_t b = 0; b < hp.batches.size(); ++b) {
         const Batch& hb = hp.batches[b];
         BatchDevSet& db = p->dbatches[b];
@@ -334,6 +340,9 @@ static int upload_batches(tcc_plan* p) {
                     r.smem_il = db.rev.lean ? lean_smem_bytes(xa[2], cols, db.nops, 3) : 0;
                     r.max_rows = xa[2];
                     r.max_cols = cols;
+                    if (db.fwd.lean && p->persist_fwd) persist_config(1, p->batch_threads, xa[2], cols, db.nops, &r.smem_p_fwd, &r.ctas_p_fwd);
+                    if (db.rev.lean && p->persist_rev && p->rev_interleave)
+                        persist_config(3, p->batch_threads_rev, xa[2], cols, db.nops, &r.smem_p_rev, &r.ctas_p_rev);
                     db.smem_fwd = std::max(db.smem_fwd, r.smem_fwd);
                     db.smem_rev = std::max(db.smem_rev, r.smem_rev);
                     if (r.pa_cnt > 0 && r.pb_cnt > 0) out->push_back(r);
@@ -460,7 +469,10 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
     p->lean = env_int("TCC_B200_LEAN", 1) != 0 && p->batch_threads == p->batch_threads_rev && (p->batch_threads & (p->batch_threads - 1)) == 0 &&
               p->batch_threads >= 64;
     p->rev_interleave = p->lean && env_int("TCC_B200_REV_IL", 1) != 0;
-    p->lean_fwd = p->lean && env_int("TCC_B200_LEAN_FWD", 0) != 0;
+    p->persist_rev = env_int("TCC_B200_PERSIST", 1) != 0;
+    p->sigma_overlap = env_int("TCC_B200_SIGMA_OVERLAP", 0) != 0;
+    p->persist_fwd = p->lean && env_int("TCC_B200_PERSIST_FWD", 0) != 0;
+    p->lean_fwd = p->lean && (env_int("TCC_B200_LEAN_FWD", 0) != 0 || p->persist_fwd);
     p->hp.error.clear();
     p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0, rank, world, p->lean ? p->batch_threads : 0,
                    env_int("TCC_B200_DYN_LAYOUT", 0) != 0 && world == 1);
@@ -495,6 +507,9 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
         return code;
     };
     if (int rc_dev = use_device(p)) return bail(rc_dev);
+    cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaMalloc(&p->persist_ctl, sizeof(unsigned) * 64) != cudaSuccess) return bail(TCC_ERR_CUDA);
+    cudaMemset(p->persist_ctl, 0, sizeof(unsigned) * 64);
     for (size_t h = 0; h < p->hp.hops.size(); ++h)
         if (upload_hop(p, int(h))) return bail(TCC_ERR_CUDA);
     if (int rc2 = upload_batches(p)) return bail(rc2);
@@ -571,6 +586,7 @@ void tcc_plan_destroy(tcc_plan* p) {
     cudaFree(p->ws2);
     cudaFree(p->kb);
     cudaFree(p->kb2);
+    cudaFree(p->persist_ctl);
     cudaFree(p->dyn_f);
     cudaFree(p->d_dyn_init);
     cudaFree(p->io1);
@@ -791,6 +807,29 @@ static int apply_h_sets(tcc_plan* p, const double* c, double* sigma, double* ws1
         return 0;
     }
     const int64_t vec = hp.N * 8 * n_sets;
+    if (p->sigma_overlap && !p->fan.aux.empty()) {
+        // Two streams: the beta-beta part (transpose, ELL SpMM on the transposed matrix: L2-bound) runs beside the
+        // alpha-beta kernel (FP64 tensor pipe, shared memory); sigma is zeroed first, the alpha-beta kernel adds into it
+        // with fp64 reductions, the alpha-alpha SpMM then accumulates row by row, the transposed beta-beta result last.
+        cudaStream_t sb = p->fan.aux[0];
+        cudaEventRecord(p->fan.start, st);
+        cudaStreamWaitEvent(sb, p->fan.start, 0);
+        launch_transpose(c, ws1, hp.na, hp.nb, false, n_sets, sb);
+        launch_spmm_rows(ws1, ws2, hp.nb, hp.na, p->d_ell_col, p->d_ell_val, hp.ell_width, false, n_sets, sb);
+        cudaEventRecord(p->fan.done[0], sb);
+        p->prof.mark(TCC_PROF_SIGMA_AB, st);
+        cudaMemsetAsync(sigma, 0, size_t(vec), st);
+        launch_sigma_ab(c, sigma, hp.na, hp.nb, p->d_links, hp.ml, p->d_w, hp.n, p->n2p, p->d_kmap, n_sets, st);
+        p->prof.count(TCC_PROF_SIGMA_AB, (hp.na + 65534) / 65535, 3 * vec);
+        p->prof.mark(TCC_PROF_SIGMA_SS, st);
+        launch_spmm_rows(c, sigma, hp.na, hp.nb, p->d_ell_col, p->d_ell_val, hp.ell_width, true, n_sets, st);
+        cudaStreamWaitEvent(st, p->fan.done[0], 0);
+        launch_transpose(ws2, sigma, hp.nb, hp.na, true, n_sets, st);
+        p->prof.count(TCC_PROF_SIGMA_SS, 4, 9 * vec);
+        p->prof.mark(-1, st);
+        p->launches += 5 + (hp.na + 65534) / 65535;
+        return 0;
+    }
     // alpha-alpha: sigma(a', :) = sum_a Hss[a', a] c(a, :)
     p->prof.mark(TCC_PROF_SIGMA_SS, st);
     launch_spmm_rows(c, sigma, hp.na, hp.nb, p->d_ell_col, p->d_ell_val, hp.ell_width, false, n_sets, st);
@@ -869,7 +908,8 @@ static int forward_sweep(tcc_plan* p, const double* params, double* vec, cudaStr
         for (size_t b = 0; b < nbt; ++b) {
             BatchDevSet& db = p->dbatches[b];
             if (p->btimer.on) cudaEventRecord(p->btimer.ev[b], st);
-            launch_batch_forward(cur, other, hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
+            launch_batch_forward(cur, other, hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st, &p->fan,
+                                 p->persist_ctl, p->sms);
             if (other) std::swap(cur, other);
             p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * hp.N);
             p->launches += 1;
@@ -889,6 +929,9 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
         // d_rot_rev was uploaded together with d_rot_fwd by the forward sweep of the same parameters
         p->prof.mark(TCC_PROF_REV_BATCH, st);
         const int nbt = int(p->dbatches.size());
+        // ticket counters of the persistent launches: self-resetting, cleared here anyway so that an aborted launch of an
+        // earlier evaluation cannot leak into this one
+        cudaMemsetAsync(p->persist_ctl, 0, sizeof(unsigned) * 64, st);
         // Interleaved mode: (ket, bra) become one 16-byte element per determinant for the whole sweep (one pass to
         // build it; nothing is converted back -- only the gradients leave the sweep).  Batches without lean streams
         // (a side without active orbitals) work on the two vectors: the data is converted around them.
@@ -936,7 +979,7 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
                     in_kb = true;
                 }
                 launch_batch_reverse_il(kb_cur, kb_other, hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart,
-                                        p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
+                                        p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan, p->persist_ctl, p->sms);
                 if (kb_other) std::swap(kb_cur, kb_other);
             } else {
                 if (in_kb) {
@@ -1434,7 +1477,7 @@ int tcc_shard_forward(tcc_plan* p, int seg, double* vec_local_dev, void* stream)
     for (int b = s.batch_lo; b < s.batch_hi; ++b) {
         BatchDevSet& db = p->dbatches[b];
         launch_batch_forward(vec_local_dev, nullptr, p->hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st,
-                             &p->fan);
+                             &p->fan, p->persist_ctl, p->sms);
         p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
         p->launches += 1;
     }
@@ -1475,11 +1518,12 @@ int tcc_shard_reverse_interleaved(tcc_plan* p, int seg, double* kb_local_dev, vo
     const Segment& s = p->hp.segments[seg];
     for (int b = s.batch_lo; b < s.batch_hi; ++b)
         if (!p->dbatches[b].rev.lean) return fail(TCC_ERR_BAD_ARGUMENT, "segment holds a batch without lean streams");
+    cudaMemsetAsync(p->persist_ctl, 0, sizeof(unsigned) * 64, st);
     p->prof.mark(TCC_PROF_REV_BATCH, st);
     for (int b = s.batch_hi - 1; b >= s.batch_lo; --b) {
         BatchDevSet& db = p->dbatches[b];
         launch_batch_reverse_il(kb_local_dev, nullptr, p->hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart,
-                                p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan);
+                                p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan, p->persist_ctl, p->sms);
         p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
         p->launches += 2;
     }

@@ -385,7 +385,10 @@ void launch_spmm_rows(const double* in, double* out, int64_t nrows, int64_t ncol
 //                                                       the alpha links l of string a (E_pq|a> = sgn_l |a'_l>)
 //   3. sigma(a'_l, b') += sgn_l G[l, b']            -- coalesced fp64 reductions into the target rows
 // ------------------------------------------------------------------------------------------------
-constexpr int SAB_T = 32;
+#ifndef SAB_T_COLS
+#define SAB_T_COLS 32
+#endif
+constexpr int SAB_T = SAB_T_COLS;
 constexpr int SAB_LD = SAB_T + 4;  // LD = 4 (mod 16): the B-fragment loads of a half-warp hit 16 distinct 8-byte banks
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {

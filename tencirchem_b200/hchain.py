@@ -139,20 +139,37 @@ def canonical_mo_coeff(mo_coeff):
     return mo_coeff * sign.reshape(1, -1)
 
 
-def h_chain_integrals(n_h: int = 4, bond_distance: float = 0.8):
+def h_chain_integrals(n_h: int = 4, bond_distance: float = 0.8, with_mo_energy: bool = False):
     """MO integrals of a linear hydrogen chain in STO-3G (molecule.py:72-73; hamiltonian.py:30-48 with the full
-    space as active space).  Returns ``int1e [n,n], int2e [n,n,n,n] (chemist notation), e_nuc, e_hf``."""
+    space as active space).  Returns ``int1e [n,n], int2e [n,n,n,n] (chemist notation), e_nuc, e_hf`` and, with
+    ``with_mo_energy``, the RHF orbital energies (what MP2 needs, see :func:`mp2_t2`)."""
     if n_h % 2:
         raise ValueError("UCC class does not support open shell system")  # ucc.py:207-208
     z = np.arange(n_h) * bond_distance / BOHR
     centers = np.stack([np.zeros(n_h), np.zeros(n_h), z], axis=1)
     s, hcore, eri = ao_integrals(centers)
     e_nuc = sum(1.0 / abs(z[i] - z[j]) for i in range(n_h) for j in range(i))
-    e_el, c, _ = rhf(s, hcore, eri, n_h)
+    e_el, c, e_orb = rhf(s, hcore, eri, n_h)
     c = canonical_mo_coeff(c)
     int1e = c.T @ hcore @ c
     int2e = np.einsum("up,vq,uvls,lr,st->pqrt", c, c, eri, c, c, optimize=True)
+    if with_mo_energy:
+        return int1e, int2e, float(e_nuc), float(e_el + e_nuc), np.asarray(e_orb)
     return int1e, int2e, float(e_nuc), float(e_el + e_nuc)
+
+
+def mp2_t2(int2e, mo_energy, n_occ: int):
+    """Closed-shell MP2 doubles amplitudes in PySCF's layout and convention (what ``UCC.__init__`` takes from
+    ``mp2.kernel()``, ucc.py:259-265): ``t2[i, j, a, b] = (ia|jb) / (e_i + e_j - e_a - e_b)`` for canonical RHF
+    orbitals, and the correlation energy ``sum t2[i,j,a,b] * (2 (ia|jb) - (ib|ja))``.  Returns ``(e_corr, t2)``."""
+    int2e = np.asarray(int2e, dtype=np.float64)
+    e = np.asarray(mo_energy, dtype=np.float64)
+    o, v = slice(0, n_occ), slice(n_occ, len(e))
+    ovov = int2e[o, v, o, v]  # (ia|jb) as [i, a, j, b]
+    d = e[o][:, None, None, None] - e[v][None, :, None, None] + e[o][None, None, :, None] - e[v][None, None, None, :]
+    t_iajb = ovov / d
+    e_corr = float(np.einsum("iajb,iajb->", t_iajb, 2.0 * ovov - ovov.transpose(0, 3, 2, 1)))
+    return e_corr, np.ascontiguousarray(t_iajb.transpose(0, 2, 1, 3))
 
 
 def active_space_integrals(int1e, int2e, e_nuc, n_elec_total, active_space):

@@ -171,3 +171,38 @@ def test_bench_reference_arm_json_contract():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_mp2_screened_uccsd_matches_oracle_and_published_counts():
+    """MP2-screened, amplitude-sorted UCCSD (uccsd.py:107-178, the reference's default ansatz): the product's ex_ops /
+    param_ids / init_guess against the oracle restatement (which goes through the full spatial2spin tensor), the MP2
+    energy of H4 and the H2 initial guess the reference prints, and the parameter counts of its quickstart table
+    (docs/source/quickstart.rst:75-104: 11 / 39 / 108 / 246 / 495)."""
+    from oracle import pools as OP
+    from tencirchem_b200.ansatz import UCCSD
+    from tencirchem_b200.hchain import h_chain_integrals, mp2_t2
+
+    int1e, int2e, e_nuc, e_hf, e_orb = h_chain_integrals(2, 0.741, True)
+    e_corr, t2 = mp2_t2(int2e, e_orb, 1)
+    u = UCCSD(int1e, int2e, 2, e_nuc, t2=t2)
+    assert u.ex_ops == [(3, 2), (1, 0), (1, 3, 2, 0)] and u.param_ids == [0, 0, 1]  # uccsd.py:139-144
+    assert abs(u.init_guess[1] - (-0.07260814651571333)) < 1e-12  # ucc_functions.ipynb:115
+    published = {4: 11, 6: 39, 8: 108, 10: 246, 12: 495}
+    for n, n_params in published.items():
+        int1e, int2e, e_nuc, e_hf, e_orb = h_chain_integrals(n, 0.8, True)
+        e_corr, t2 = mp2_t2(int2e, e_orb, n // 2)
+        if n == 4:
+            assert abs(e_hf + e_corr - (-2.151794)) < 5e-7  # adapt_vqe.ipynb:411
+        u = UCCSD(int1e, int2e, n, e_nuc, t2=t2)
+        assert u.n_params == n_params
+        if n <= 8:
+            e_o, t2_o = OP.mp2_t2(int2e, e_orb, n // 2)
+            assert abs(e_o - e_corr) < 1e-12 and np.abs(t2_o - t2).max() < 1e-13
+            ops, pids, guess = OP.uccsd_ex_ops_screened(n // 2, n // 2, t2)
+            assert u.ex_ops == ops and list(u.param_ids) == pids
+            assert np.abs(np.asarray(u.init_guess) - np.asarray(guess)).max() < 1e-15
+            for pick, sort in [(False, True), (True, False), (False, False)]:
+                v = UCCSD(int1e, int2e, n, e_nuc, t2=t2, pick_ex2=pick, sort_ex2=sort)
+                ops, pids, guess = OP.uccsd_ex_ops_screened(n // 2, n // 2, t2, pick, sort)
+                assert v.ex_ops == ops and list(v.param_ids) == pids
+                assert np.abs(np.asarray(v.init_guess) - np.asarray(guess)).max() < 1e-15

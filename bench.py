@@ -396,7 +396,7 @@ def run_b200(args):
                     "fwd_alpha": "rotate_kernel<false,true>", "fwd_beta": "rotate_kernel<true,false>",
                     "sigma_ab": "sigma_ab_kernel", "sigma_ss": "spmm_rows_kernel+transpose_kernel", "dot": "dot_kernel",
                     "fwd_batch": "batch_kernel<1> (one launch per batch of excitations, whole vector read+written once)",
-                    "rev_batch": "batch_kernel<2> (+ batch_grad_reduce_kernel; ket and bra read+written once per batch)"}
+                    "rev_batch": "lean_persist_kernel<3> (+ batch_grad_reduce_kernel; interleaved (ket, bra) elements read+written once per batch)"}
     total_prof_ms = sum(v[0] for v in prof.values())
     phases = {s: {"ms_per_step": round(v[0] / args.steps, 3), "launches_per_step": v[1] // args.steps,
                   "algorithmic_GBps": round(v[2] / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 else None,
@@ -541,7 +541,7 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
                 "d2h_bytes_per_step": 8 * (m + 1) * world,
                 "note": "ShardedUCC.energy_and_grad(params): host params in, host (energy, gradient) out on every rank; wall clock"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "batch_kernel<2> (rank 0's share of the rows)" if dom == "rev_batch" else dom,
+        "roofline": {"bound": "hbm", "kernel": "lean_persist_kernel<3> (rank 0's share of the rows)" if dom == "rev_batch" else dom,
                      "phase": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": None,
                      "avg_launch_us": 1e3 * d_ms / max(d_launch, 1), "launches": d_launch,

@@ -145,7 +145,6 @@ struct tcc_plan {
     int lean = 1;           // lean per-thread streams for two-sided batches (TCC_B200_LEAN=0: the plain pair lists)
     int lean_fwd = 0;       // forward sweep on the lean kernel too (TCC_B200_LEAN_FWD=1); measured slower than batch_kernel<1>
     int rev_interleave = 1; // reverse sweep on interleaved (ket, bra) elements (TCC_B200_REV_IL=0: two vectors)
-    int sigma_overlap = 0;  // H.c on two streams (TCC_B200_SIGMA_OVERLAP=1), see apply_h_sets
     int persist_rev = 1;    // reverse sweep on the persistent kernel (lean_persist_kernel<3>; TCC_B200_PERSIST=0: one tile per CTA)
     int persist_fwd = 0;    // forward sweep on lean_persist_kernel<1> (TCC_B200_PERSIST_FWD=1; needs the lean forward streams)
     unsigned* persist_ctl = nullptr;  // ticket counters of the persistent launches [2][16][2], self-resetting
@@ -470,10 +469,10 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
               p->batch_threads >= 64;
     p->rev_interleave = p->lean && env_int("TCC_B200_REV_IL", 1) != 0;
     p->persist_rev = env_int("TCC_B200_PERSIST", 1) != 0;
-    p->sigma_overlap = env_int("TCC_B200_SIGMA_OVERLAP", 0) != 0;
     p->persist_fwd = p->lean && env_int("TCC_B200_PERSIST_FWD", 0) != 0;
     p->lean_fwd = p->lean && (env_int("TCC_B200_LEAN_FWD", 0) != 0 || p->persist_fwd);
     p->hp.error.clear();
+    p->hp.sched_mode = env_int("TCC_B200_SCHED", 0);
     p->hp.finalize(env_int("TCC_B200_TILE_ELEMS", 6144), env_int("TCC_B200_LAYOUT", 1) != 0, rank, world, p->lean ? p->batch_threads : 0,
                    env_int("TCC_B200_DYN_LAYOUT", 0) != 0 && world == 1);
     if (!p->hp.error.empty()) {
@@ -807,29 +806,6 @@ static int apply_h_sets(tcc_plan* p, const double* c, double* sigma, double* ws1
         return 0;
     }
     const int64_t vec = hp.N * 8 * n_sets;
-    if (p->sigma_overlap && !p->fan.aux.empty()) {
-        // Two streams: the beta-beta part (transpose, ELL SpMM on the transposed matrix: L2-bound) runs beside the
-        // alpha-beta kernel (FP64 tensor pipe, shared memory); sigma is zeroed first, the alpha-beta kernel adds into it
-        // with fp64 reductions, the alpha-alpha SpMM then accumulates row by row, the transposed beta-beta result last.
-        cudaStream_t sb = p->fan.aux[0];
-        cudaEventRecord(p->fan.start, st);
-        cudaStreamWaitEvent(sb, p->fan.start, 0);
-        launch_transpose(c, ws1, hp.na, hp.nb, false, n_sets, sb);
-        launch_spmm_rows(ws1, ws2, hp.nb, hp.na, p->d_ell_col, p->d_ell_val, hp.ell_width, false, n_sets, sb);
-        cudaEventRecord(p->fan.done[0], sb);
-        p->prof.mark(TCC_PROF_SIGMA_AB, st);
-        cudaMemsetAsync(sigma, 0, size_t(vec), st);
-        launch_sigma_ab(c, sigma, hp.na, hp.nb, p->d_links, hp.ml, p->d_w, hp.n, p->n2p, p->d_kmap, n_sets, st);
-        p->prof.count(TCC_PROF_SIGMA_AB, (hp.na + 65534) / 65535, 3 * vec);
-        p->prof.mark(TCC_PROF_SIGMA_SS, st);
-        launch_spmm_rows(c, sigma, hp.na, hp.nb, p->d_ell_col, p->d_ell_val, hp.ell_width, true, n_sets, st);
-        cudaStreamWaitEvent(st, p->fan.done[0], 0);
-        launch_transpose(ws2, sigma, hp.nb, hp.na, true, n_sets, st);
-        p->prof.count(TCC_PROF_SIGMA_SS, 4, 9 * vec);
-        p->prof.mark(-1, st);
-        p->launches += 5 + (hp.na + 65534) / 65535;
-        return 0;
-    }
     // alpha-alpha: sigma(a', :) = sum_a Hss[a', a] c(a, :)
     p->prof.mark(TCC_PROF_SIGMA_SS, st);
     launch_spmm_rows(c, sigma, hp.na, hp.nb, p->d_ell_col, p->d_ell_val, hp.ell_width, false, n_sets, st);

@@ -226,9 +226,28 @@ int64_t HostPlan::max_class(int m) const {
 }
 
 std::vector<std::vector<int>> HostPlan::group_ops(int tile_elems) const {
-    // Greedy list scheduling.  An excitation joins the open batch if the enlarged active sets still give
-    // tiles that fit on chip AND it commutes with every excitation that was skipped before it (disjoint
-    // spin-orbital sets => the generators commute), so the product of factors is unchanged.
+    if (sched_mode == 2) {  // both schedulers, the one with fewer batches (ties: first come, first served)
+        HostPlan* self = const_cast<HostPlan*>(this);
+        self->sched_mode = 0;
+        std::vector<std::vector<int>> g0 = group_ops(tile_elems);
+        self->sched_mode = 1;
+        std::vector<std::vector<int>> g1 = group_ops(tile_elems);
+        self->sched_mode = 2;
+        return g1.size() < g0.size() ? g1 : g0;
+    }
+    // List scheduling.  A batch is described by its active sets (S_alpha, S_beta); given the sets, one pass over the
+    // remaining excitations in order takes every excitation that lies inside them AND commutes with every excitation
+    // skipped before it (disjoint spin-orbital sets => the generators commute), so the product of factors is unchanged.
+    // sched_mode 0 grows the sets first come, first served: the union with each excitation met in order while the
+    // tiles still fit on chip -- good for the generator order of the ansatz classes, where neighbours share orbitals.
+    // sched_mode 1 chooses the sets: starting from the first remaining excitation (it must run now), the
+    // union with that one of the next candidates is taken which lets the pass capture the most excitations, until no
+    // candidate helps.  For amplitude-sorted lists (the reference's default UCCSD, uccsd.py:159-178), whose neighbours
+    // are unrelated, this saves 7 % of the batches (492 instead of 530 for the screened H16 ansatz; 253 instead of
+    // 258 for unscreened (16e,16o) UCCSD) -- the dependency chains of such a list are dense (two random opposite-spin
+    // doubles share an orbital with probability 0.43), so few excitations are ever free to move -- and the batches it builds are
+    // SLOWER per batch at (16e,16o) (forward 351 vs 341 ms, reverse 678 vs 664 ms for the whole sweep: other active sets,
+    // other storage order), so sched_mode 0 stays the default.  sched_mode 2 runs both and keeps the shorter schedule.
     std::vector<std::vector<int>> groups;
     std::vector<int> remaining(ops.size());
     std::iota(remaining.begin(), remaining.end(), 0);
@@ -238,9 +257,76 @@ std::vector<std::vector<int>> HostPlan::group_ops(int tile_elems) const {
     int64_t side_cap = 64;
     while (side_cap * side_cap < 4 * int64_t(tile_elems)) ++side_cap;  // 2 * sqrt(tile_elems)
     if (hcb) side_cap = tile_elems;
+    auto fits = [&](uint32_t nsa, uint32_t nsb) {
+        const int64_t ca = max_class(hcb ? 0 : popc(nsa)), cb = max_class(popc(nsb));
+        // keep tiles roughly square: a long thin tile has row segments too short to coalesce
+        // sharded plans: log2(world) alpha orbitals must stay inactive, they carry the row layout of the batch
+        const bool rows_ok = shard_world == 1 || popc(nsa) + shard_bits() <= n;
+        return ca * cb <= tile_elems && ca <= side_cap && cb <= side_cap && rows_ok;
+    };
+    // number of excitations the in-order pass captures with FIXED active sets
+    auto captured = [&](uint32_t sa, uint32_t sb) {
+        uint32_t skip_a = 0, skip_b = 0;
+        size_t cnt = 0;
+        const size_t lim = std::min(remaining.size(), window);
+        for (size_t i = 0; i < lim && cnt < max_ops; ++i) {
+            const OpDesc& op = ops[remaining[i]];
+            const uint32_t oa = op.cre_a | op.ann_a, ob = op.cre_b | op.ann_b;
+            if (!((oa & skip_a) || (ob & skip_b)) && !(oa & ~sa) && !(ob & ~sb)) {
+                ++cnt;
+                continue;
+            }
+            skip_a |= oa;
+            skip_b |= ob;
+            if ((hcb || skip_a == all) && skip_b == all) break;
+        }
+        return cnt;
+    };
     while (!remaining.empty()) {
         std::vector<int> batch, rest;
         uint32_t sa = 0, sb = 0, skip_a = 0, skip_b = 0;
+        bool fixed_sets = false;
+        if (sched_mode == 1) {
+            const OpDesc& first = ops[remaining[0]];
+            sa = first.cre_a | first.ann_a;
+            sb = first.cre_b | first.ann_b;
+            size_t best = captured(sa, sb);
+            const size_t n_cand = 64;
+            for (;;) {
+                // candidates: the next excitations (in order) that are not inside the sets, not blocked by an excitation
+                // outside them, and whose union still fits
+                uint32_t ka = 0, kb = 0, best_a = 0, best_b = 0;
+                size_t seen = 0, best_cnt = best;
+                int best_grow = 1 << 30;
+                const size_t lim = std::min(remaining.size(), window);
+                for (size_t i = 0; i < lim && seen < n_cand; ++i) {
+                    const OpDesc& op = ops[remaining[i]];
+                    const uint32_t oa = op.cre_a | op.ann_a, ob = op.cre_b | op.ann_b;
+                    const bool inside = !(oa & ~sa) && !(ob & ~sb);
+                    const bool blocked = (oa & ka) || (ob & kb);
+                    if (inside && !blocked) continue;
+                    if (!blocked && fits(sa | oa, sb | ob)) {
+                        ++seen;
+                        const size_t c = captured(sa | oa, sb | ob);
+                        const int grow = popc((sa | oa) ^ sa) + popc((sb | ob) ^ sb);
+                        if (c > best_cnt || (c == best_cnt && c > best && grow < best_grow)) {
+                            best_cnt = c;
+                            best_grow = grow;
+                            best_a = sa | oa;
+                            best_b = sb | ob;
+                        }
+                    }
+                    ka |= oa;
+                    kb |= ob;
+                    if ((hcb || ka == all) && kb == all) break;
+                }
+                if (best_cnt <= best) break;
+                best = best_cnt;
+                sa = best_a;
+                sb = best_b;
+            }
+            fixed_sets = true;
+        }
         bool closed = false;
         for (size_t i = 0; i < remaining.size(); ++i) {
             int j = remaining[i];
@@ -253,11 +339,8 @@ std::vector<std::vector<int>> HostPlan::group_ops(int tile_elems) const {
             bool blocked = (oa & skip_a) || (ob & skip_b);
             if (!blocked) {
                 uint32_t nsa = sa | oa, nsb = sb | ob;
-                int64_t ca = max_class(hcb ? 0 : popc(nsa)), cb = max_class(popc(nsb));
-                // keep tiles roughly square: a long thin tile has row segments too short to coalesce
-                // sharded plans: log2(world) alpha orbitals must stay inactive, they carry the row layout of the batch
-                const bool rows_ok = shard_world == 1 || popc(nsa) + shard_bits() <= n;
-                if ((ca * cb <= tile_elems && ca <= side_cap && cb <= side_cap && rows_ok) || batch.empty()) {
+                const bool ok = fixed_sets ? (nsa == sa && nsb == sb) : fits(nsa, nsb);
+                if (ok || batch.empty()) {
                     batch.push_back(j);
                     sa = nsa;
                     sb = nsb;

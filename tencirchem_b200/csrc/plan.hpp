@@ -170,6 +170,8 @@ struct HostPlan {
         return t;
     }
     int n_params = 0;
+    int sched_mode = 0;  // batch scheduler (group_ops): 0 = active sets grown first come first served (default), 1 = chosen
+                         // for the most excitations, 2 = whichever gives fewer batches
     std::string error;
     // DYNAMIC COLUMN LAYOUT (whole-vector plans).  In the static storage order a beta class of a batch is contiguous
     // only when the active beta orbitals of the batch happen to sit in the lowest bit positions; over a UCCSD sweep the

@@ -279,10 +279,18 @@ class ShardPool:
         self.p2p = self.peer_ptrs[0] is not None
         self._used = [False] * self.n_slots
         self._owner = {}  # data_ptr of local rank 0's view -> (first slot, number of slots)
+        # stream barriers seen so far, and for every slot the count at its last release: a slot released BEFORE the last
+        # barrier is idle on every rank (all ranks run the same program), so peers may write into it without another one
+        self.barriers = 0
+        self._released_at = [-1] * self.n_slots
 
     def reset(self):
         self._used = [False] * self.n_slots
         self._owner.clear()
+        self._released_at = [self.barriers] * self.n_slots
+
+    def idle_everywhere(self, first: int, n: int) -> bool:
+        return all(self._released_at[j] < self.barriers for j in range(first, first + n))
 
     def _take(self, n: int) -> int:
         run = 0
@@ -331,6 +339,7 @@ class ShardPool:
         if got is not None:
             for j in range(got[0], got[0] + got[1]):
                 self._used[j] = False
+                self._released_at[j] = self.barriers
 
 
 class RowMover:
@@ -419,9 +428,9 @@ class RowMover:
     def reshard(self, vecs: List["torch.Tensor"], l_from: int, l_to: int, keep_src: bool = False) -> List["torch.Tensor"]:
         """vecs[i]: local [rows, ...] block of the i-th local rank in layout l_from -> the same in layout l_to, in a
         fresh slot of the pool; the source slot is released unless keep_src.  With a peer-mapped pool every row is
-        written straight into the destination slot of its new owner (tcc_push_rows, one pass over NVLink) between two
-        stream barriers: the first makes sure every rank has finished with whatever lived in the destination slot, the
-        second that all rows have arrived.  Otherwise: pack, NCCL all-to-all, unpack in rounds of chunk_bytes."""
+        written straight into the destination slot of its new owner (tcc_push_rows, one pass over NVLink), followed by
+        a stream barrier (all rows have arrived) and preceded by one only when the destination slot was released since the
+        last barrier (otherwise every rank is known to have finished with whatever lived there).  Otherwise: pack, NCCL all-to-all, unpack in rounds of chunk_bytes."""
         import ctypes as C
 
         from . import _lib
@@ -439,10 +448,12 @@ class RowMover:
         else:
             out = pool.empty(new_rows, trailing)
         if pool is not None and pool.p2p:
-            first, _ = pool.slot_of(out)
+            first, n_dst = pool.slot_of(out)
             nbytes = sum(int(v.numel()) * 8 for v in vecs)
-            with self.timer.phase("move_barrier"):
-                self.comm.stream_barrier()
+            if not pool.idle_everywhere(first, n_dst):
+                with self.timer.phase("move_barrier"):
+                    self.comm.stream_barrier()
+                pool.barriers += 1
             with self.timer.phase("move_push", nbytes):
                 for k, r in enumerate(self.comm.local_ranks):
                     src_row, dst_row, dst_rank = self._push_plan(l_from, l_to, r)
@@ -453,6 +464,7 @@ class RowMover:
                             C.c_void_p(pool.peer_ptrs[k].data_ptr()), first * pool.slot, self._stream()))
             with self.timer.phase("move_barrier"):
                 self.comm.stream_barrier()
+            pool.barriers += 1
         else:
             plans = [self._move_plan(l_from, l_to, r, row_elems) for r in self.comm.local_ranks]
             for j in range(len(plans[0][0])):

@@ -306,6 +306,41 @@ def test_small_tiles_many_batches(tile_elems, threads, monkeypatch):
     clear_cache()
 
 
+@pytest.mark.parametrize("persist,persist_fwd,sched", [("1", "1", "2"), ("0", "0", "0"), ("1", "0", "1")])
+@pytest.mark.parametrize("tile_elems", [64, 400, 6144])
+def test_persistent_kernels_and_schedulers_against_oracle(tile_elems, persist, persist_fwd, sched, monkeypatch):
+    """The persistent batch kernel (lean_persist_kernel: ticketed tiles, next tile resolved during the gather) in the
+    reverse sweep (default) AND in the forward sweep (TCC_B200_PERSIST_FWD=1), the classic one-tile-per-CTA kernels
+    (TCC_B200_PERSIST=0), and the three batch schedulers (TCC_B200_SCHED), from a handful to thousands of tiles per
+    launch (more tiles than resident CTAs, so every CTA takes several tickets): state, energy, gradient, with an
+    init_state, twice in a row (the ticket counters reset themselves between launches)."""
+    monkeypatch.setenv("TCC_B200_TILE_ELEMS", str(tile_elems))
+    monkeypatch.setenv("TCC_B200_PERSIST", persist)
+    monkeypatch.setenv("TCC_B200_PERSIST_FWD", persist_fwd)
+    monkeypatch.setenv("TCC_B200_SCHED", sched)
+    clear_cache()
+    for kind, no, nv in [("uccsd", 4, 4), ("uccsd", 2, 4), ("kupccgsd", 3, 3)]:
+        ucc, int1e, int2e = _build(kind, no, nv)
+        params = _params(ucc.n_params)
+        rng = np.random.default_rng(11)
+        init = rng.standard_normal(ucc.civector_size)
+        init /= np.linalg.norm(init)
+        plan = Plan(ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids)
+        plan.set_hamiltonian(int1e, int2e)
+        h = O.get_h_from_integral(int1e, int2e, ucc.n_elec, False)
+        e_ref, g_ref = O.get_energy_and_grad(params, h, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False)
+        ei_ref, gi_ref = O.get_energy_and_grad(params, h, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False, init_state=init)
+        c_ref = O.get_civector(params, ucc.n_qubits, ucc.n_elec, ucc.ex_ops, ucc.param_ids, False)
+        for _ in range(2):
+            e, g = plan.energy_and_grad(params)
+            assert abs(e - e_ref) < E_TOL and np.abs(g - g_ref).max() < G_TOL
+            ei, gi = plan.energy_and_grad(params, init)
+            assert abs(ei - ei_ref) < E_TOL and np.abs(gi - gi_ref).max() < G_TOL
+            assert np.abs(plan.civector(params) - c_ref).max() < C_TOL
+        O.clear_cache()
+    clear_cache()
+
+
 @pytest.mark.parametrize("tile_elems", [64, 400, 1500])
 def test_dynamic_column_layout_against_static_and_oracle(tile_elems, monkeypatch):
     """Dynamic column layout (every batch gathers its tiles from contiguous columns and scatters in the order of the

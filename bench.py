@@ -531,10 +531,12 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
                    "n_determinants": size, "n_excitations": m,
                    "n_params": p_count, "l2": "inputs larger than L2 (ket + bra shards vs 126 MB)" if 2 * size * 8 / world > 1.26e8 else "vectors fit in L2; no flush",
                    "multi_gpu": f"one evaluation, CI vector sharded by alpha rows over {world} ranks; {reshards} row re-shards "
-                                f"(NCCL all-to-all) per evaluation in {len(eng.segments)} segments; "
+                                + ("(rows written straight into the peers' shard pool over NVLink, tcc_push_rows) " if getattr(eng.pool, "p2p", False)
+                                   else "(pack, NCCL all-to-all, unpack) ")
+                                + f"per evaluation in {len(eng.segments)} segments; "
                                 + ("H.c with the vector kept sharded (3 alpha-beta passes on per-layout link tables, alpha-alpha on "
                                    "column blocks, beta-beta local)" if eng.sigma_mode == "distributed" else
-                                   "H.c by row blocks of the all-reduced vector")
+                                   "H.c by row blocks of the all-gathered vector, result reduce-scattered")
                                 + "; gradient and energy all-reduced",
                    "n_batches": plan.n_batches, "staging_s": round(staging_s, 2)},
         "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": 8 * p_count * world,

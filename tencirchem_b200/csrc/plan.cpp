@@ -2,6 +2,7 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -574,6 +575,119 @@ static void bank_ordered(const std::vector<uint32_t>& raw, int group, std::vecto
     }
 }
 
+// Conflict-free groups by bipartite matching (lean streams).  A group of `group` consecutive stream entries is what one
+// quarter-warp (16-byte elements, group = 8) or half-warp (8-byte elements, group = 16) sends to shared memory in one
+// wavefront -- if the first elements of the group fall into `group` different banks and the second elements too; ONE
+// clash costs the whole group a second wavefront, which is why the greedy order above still leaves 1.43 wavefronts per
+// ideal one (host model = ncu, profiles/r02_reverse_kernel_breakdown.md).  Here the entries are bucketed by (bank of the
+// first element, bank of the second element); a group is a perfect matching between the first-element banks and the
+// second-element banks over the non-empty buckets (Kuhn's augmenting paths on a group x group graph, fullest buckets
+// first so that the buckets drain evenly).  When no perfect matching is left, the remaining entries form maximum
+// matchings padded with invalid entries while the stream has spare slots (`capacity` - raw.size(): the last round of an
+// excitation is rarely full), and only then groups with clashes.  The stream is emitted in whole groups.
+static void bank_matched(const std::vector<uint32_t>& raw, int group, size_t capacity, size_t last_round_at, std::vector<uint32_t>* out) {
+    const uint32_t gm = uint32_t(group - 1);
+    const size_t start = out->size();
+    const int G = group;
+    std::vector<std::vector<uint32_t>> bucket(size_t(G) * G);
+    {
+        // Which end of a pair is "first" is free: (i1, i2, sign) and (i2, i1, -sign) are the same rotation, bit for bit
+        // (x' = c x + p y, y' = c y - p x with x <-> y, p -> -p).  Each pair is oriented so that the banks are used
+        // evenly as first and as second element: the number of perfect groups is bounded by the rarest bank.
+        std::vector<int> c1(G, 0), c2(G, 0);
+        for (uint32_t e : raw) {
+            const uint32_t i1 = e & 0x7fffu, i2 = (e >> 15) & 0x7fffu, sg = (e >> 30) & 1u;
+            const int x = int(i1 & gm), y = int(i2 & gm);
+            if (std::max(c1[y], c2[x]) < std::max(c1[x], c2[y])) {
+                e = i2 | (i1 << 15) | ((sg ^ 1u) << 30);
+                ++c1[y];
+                ++c2[x];
+            } else {
+                ++c1[x];
+                ++c2[y];
+            }
+            bucket[size_t(e & gm) * G + ((e >> 15) & gm)].push_back(e);
+        }
+    }
+    size_t left = raw.size();
+    size_t spare = capacity > raw.size() ? capacity - raw.size() : 0;
+    std::vector<int> match2(G), order(G), cand(G);
+    std::vector<char> seen(G);
+    // Kuhn: try to give first-bank b1 a second-bank, fullest bucket first
+    struct Kuhn {
+        int G;
+        std::vector<std::vector<uint32_t>>* bucket;
+        std::vector<int>* match2;
+        std::vector<char>* seen;
+        bool go(int b1) {
+            int idx[32];
+            int n = 0;
+            for (int b2 = 0; b2 < G; ++b2)
+                if (!(*bucket)[size_t(b1) * G + b2].empty() && !(*seen)[b2]) idx[n++] = b2;
+            std::sort(idx, idx + n, [&](int x, int y) { return (*bucket)[size_t(b1) * G + x].size() > (*bucket)[size_t(b1) * G + y].size(); });
+            for (int i = 0; i < n; ++i) {
+                const int b2 = idx[i];
+                if ((*seen)[b2]) continue;
+                (*seen)[b2] = 1;
+                if ((*match2)[b2] < 0 || go((*match2)[b2])) {
+                    (*match2)[b2] = b1;
+                    return true;
+                }
+            }
+            return false;
+        }
+    } kuhn{G, &bucket, &match2, &seen};
+    while (left > 0) {
+        // first-element banks with the fewest alternatives go first
+        for (int b1 = 0; b1 < G; ++b1) {
+            order[b1] = b1;
+            int n = 0;
+            for (int b2 = 0; b2 < G; ++b2) n += !bucket[size_t(b1) * G + b2].empty();
+            cand[b1] = n;
+        }
+        std::sort(order.begin(), order.end(), [&](int x, int y) { return cand[x] < cand[y]; });
+        std::fill(match2.begin(), match2.end(), -1);
+        int matched = 0;
+        for (int i = 0; i < G; ++i) {
+            if (cand[order[i]] == 0) continue;
+            std::fill(seen.begin(), seen.end(), 0);
+            if (kuhn.go(order[i])) ++matched;
+        }
+        if (matched == 0) break;
+        size_t pads = size_t(G - matched);
+        for (int b2 = 0; b2 < G; ++b2)
+            if (match2[b2] >= 0) {
+                std::vector<uint32_t>& bk = bucket[size_t(match2[b2]) * G + b2];
+                out->push_back(bk.back());
+                bk.pop_back();
+                --left;
+            }
+        if (pads == 0 || left == 0) continue;
+        // an incomplete group: invalid entries may only stand in the LAST round of the stream (a lane with an entry in
+        // round r has entries in all rounds before it -- the kernels rely on that) and only while slots are spare;
+        // otherwise the group is completed with entries that clash
+        const bool last_round = out->size() - start >= last_round_at;
+        if (last_round && pads <= spare) {
+            for (size_t i = 0; i < pads; ++i) out->push_back(0u);
+            spare -= pads;
+        } else {
+            for (auto& bk : bucket) {
+                while (pads > 0 && !bk.empty()) {
+                    out->push_back(bk.back());
+                    bk.pop_back();
+                    --left;
+                    --pads;
+                }
+                if (pads == 0) break;
+            }
+        }
+    }
+    if (left > 0) {  // what could not be grouped without clashes and without padding, in bucket order
+        for (auto& bk : bucket)
+            for (uint32_t e : bk) out->push_back(e);
+    }
+}
+
 void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch* out, int lean_threads) {
     const uint32_t sa = out->sa, sb = out->sb;  // set by finalize (active_sets)
     int64_t ca = max_class(hcb ? 0 : popc(sa)), cb = max_class(popc(sb));
@@ -699,6 +813,8 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
     for (const auto& pd : out->A.panels) ga_nom[pd.e] = std::max<int>(1, pd.Gn);
     for (const auto& pd : out->B.panels) gb_nom[pd.e] = std::max<int>(1, pd.Gn);
     const bool bank_order = std::getenv("TCC_B200_BANK_ORDER") ? std::atoi(std::getenv("TCC_B200_BANK_ORDER")) != 0 : true;
+    const bool bank_match_fwd = bank_order && (std::getenv("TCC_B200_BANK_MATCH_FWD") ? std::atoi(std::getenv("TCC_B200_BANK_MATCH_FWD")) != 0 : true);
+    const bool bank_match = bank_order && (std::getenv("TCC_B200_BANK_MATCH") ? std::atoi(std::getenv("TCC_B200_BANK_MATCH")) != 0 : true);
     for (size_t t = 0; t < out->ops.size(); ++t) {
         const BatchOp& bo = out->ops[t];
         for (int ea = 0; ea <= ma; ++ea) {
@@ -715,7 +831,13 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
                 for (const Ent& a : ea_list)
                     for (const Ent& b : eb_list)
                         raw.push_back((a.s * ld + b.s) | ((a.d * ld + b.d) << 15) | ((a.sg ^ b.sg) << 30));
-                if (bank_order && raw.size() > 16)
+                if (bank_match_fwd && lean && raw.size() > 16) {
+                    // conflict-free half-warp groups by matching, completed with clashing entries where no perfect
+                    // matching is left (host model: 1.43 wavefronts per half-warp access instead of 1.77).  Padding the
+                    // incomplete groups with skip entries up to the end of the last round would reach 1.07, but the
+                    // guard and the 9 % more slots cost more than the clashes (measured: 339 ms vs 328 ms forward sweep)
+                    bank_matched(raw, 16, raw.size(), 0, &out->plist);
+                } else if (bank_order && raw.size() > 16)
                     bank_ordered(raw, 16, &taken, &out->plist);
                 else
                     out->plist.insert(out->plist.end(), raw.begin(), raw.end());
@@ -728,11 +850,15 @@ void HostPlan::build_batch(const std::vector<int>& group, int tile_elems, Batch*
                     for (int width = 0; width < 2; ++width) {
                         std::vector<uint32_t>& dst = width == 0 ? out->stream8 : out->stream16;
                         const size_t before = dst.size();
-                        if (bank_order && raw.size() > 8)
-                            bank_ordered(raw, width == 0 ? 16 : 8, &taken, &dst);
+                        const int grp = width == 0 ? 16 : 8;
+                        if (bank_match && width == 1 && raw.size() > size_t(grp) && tps % grp == 0)  // the 16-byte streams of the reverse sweep
+                            bank_matched(raw, grp, size_t(slots) * tps, size_t(slots - 1) * tps, &dst);
+                        else if (bank_order && raw.size() > 8)
+                            bank_ordered(raw, grp, &taken, &dst);
                         else
                             dst.insert(dst.end(), raw.begin(), raw.end());
-                        for (size_t i = before; i < dst.size(); ++i) dst[i] |= 0x80000000u;
+                        for (size_t i = before; i < dst.size(); ++i)
+                            if (dst[i]) dst[i] |= 0x80000000u;  // padding entries of bank_matched stay invalid
                         dst.resize(before + size_t(slots) * tps, 0u);
                     }
                 }
@@ -887,7 +1013,23 @@ void HostPlan::finalize(int tile_elems, bool use_layout, int rank, int world, in
     batches.resize(groups.size());
     for (size_t g = 0; g < groups.size(); ++g) active_sets(groups[g], tile_elems, &batches[g].sa, &batches[g].sb);
     choose_row_layouts();
-    for (size_t g = 0; g < groups.size(); ++g) build_batch(groups[g], tile_elems, &batches[g], lean_threads);
+    {
+        // the batches are independent (build_batch reads the plan and writes its own Batch): a few host threads
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned nt = unsigned(std::min<size_t>(std::min(4u, hw), groups.size()));
+        if (nt <= 1) {
+            for (size_t g = 0; g < groups.size(); ++g) build_batch(groups[g], tile_elems, &batches[g], lean_threads);
+        } else {
+            std::atomic<size_t> next{0};
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nt; ++t)
+                pool.emplace_back([&]() {
+                    for (size_t g = next.fetch_add(1); g < groups.size(); g = next.fetch_add(1))
+                        build_batch(groups[g], tile_elems, &batches[g], lean_threads);
+                });
+            for (auto& th : pool) th.join();
+        }
+    }
     if (use_dyn) build_dyn_layouts();
 }
 

@@ -515,13 +515,18 @@ def test_properties_full_size_16o(monkeypatch):
     assert abs(x_hc - c_hx) < 1e-8 * max(1.0, abs(x_hc))
     del x, hc, c
     torch.cuda.empty_cache()
-    # gradient of two parameters (one single, one opposite-spin double) against central differences of the energy
-    eps = 1e-4
+    # gradient of two parameters (one single, one opposite-spin double) against finite differences of the energy:
+    # central differences at two step sizes, Richardson-extrapolated (truncation error O(eps^4); what is left is the
+    # rounding of the energies, ~1e-13 / eps).  The north_star's 1e-8 on the gradient itself is checked against the
+    # sparse oracle at this size in tests/test_gpu_large_parity.py; this is the oracle-free cross-check.
+    eps = 2e-3
     for i in (3, ucc.n_params - 5):
         d = np.zeros_like(params)
         d[i] = eps
-        fd = (plan.energy(params + d) - plan.energy(params - d)) / (2 * eps)
-        assert abs(fd - g[i]) < 1e-6, (i, fd, g[i])
+        fd1 = (plan.energy(params + d) - plan.energy(params - d)) / (2 * eps)
+        fd2 = (plan.energy(params + 0.5 * d) - plan.energy(params - 0.5 * d)) / eps
+        fd = (4.0 * fd2 - fd1) / 3.0
+        assert abs(fd - g[i]) < 2e-8, (i, fd1, fd2, fd, g[i])
     del plan
     # the per-excitation kernels are an independent implementation of the same sweeps
     monkeypatch.setenv("TCC_B200_PER_OP", "1")

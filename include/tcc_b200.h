@@ -68,6 +68,15 @@ int tcc_num_batches(const tcc_plan* plan);
 int tcc_batch_info(const tcc_plan* plan, int b, int32_t* n_ops, int32_t* active_alpha, int32_t* active_beta,
                    int32_t* n_tiles, int32_t* max_tile_rows, int32_t* max_tile_cols,
                    int32_t* op_indices /* [n_ops of the batch] or NULL */);
+/* The pair list of the excitation at position `pos` of batch `b` for tiles whose classes hold (e_alpha, e_beta) active
+ * electrons, as the kernels read it (host-side introspection for the tests of the list ORDER: the kernels may apply the
+ * pairs of one excitation in any order and with either end first).  which = 0: the plain list of batch_kernel
+ * (entries i1 | i2 << 15 | sign << 30, tile-local element indices); 1 / 2: the per-thread streams of the lean kernels
+ * for 8-byte / 16-byte elements (the same entries | valid << 31, rounds of one entry per thread, idle slots = 0).
+ * n_out = number of entries (0 for a batch without streams), round_len (may be NULL) = entries per round of a stream
+ * (thread j of a sub-block applies entry j of every round); out_host may be NULL to query the size. */
+int tcc_batch_pairs(const tcc_plan* plan, int b, int pos, int e_alpha, int e_beta, int which, uint32_t* out_host,
+                    int capacity, int32_t* n_out, int32_t* round_len);
 /* bytes of device memory held by the plan's tables / workspaces */
 int64_t tcc_plan_device_bytes(const tcc_plan* plan);
 

@@ -38,6 +38,7 @@ SIGNATURES = {
     "tcc_plan_device_bytes": (C.c_int64, [_p]),
     "tcc_num_batches": (C.c_int, [_p]),
     "tcc_batch_info": (C.c_int, [_p, C.c_int] + [_ip] * 7),
+    "tcc_batch_pairs": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int, _ip, _ip]),
     "tcc_storage_order": (C.c_int, [_p, C.POINTER(C.c_uint32)]),
     "tcc_to_storage_order": (C.c_int, [_p, _p, _p, _p]),
     "tcc_from_storage_order": (C.c_int, [_p, _p, _p, _p]),

@@ -647,6 +647,44 @@ int tcc_batch_info(const tcc_plan* p, int b, int32_t* n_ops, int32_t* active_alp
     return 0;
 }
 
+int tcc_batch_pairs(const tcc_plan* p, int b, int pos, int e_alpha, int e_beta, int which, uint32_t* out_host, int capacity,
+                    int32_t* n_out, int32_t* round_len) {
+    if (!p || !n_out || b < 0 || b >= int(p->hp.batches.size())) return fail(TCC_ERR_BAD_ARGUMENT, "batch index out of range");
+    const Batch& hb = p->hp.batches[b];
+    const int ma = hb.A.m, mb = hb.B.m;
+    if (pos < 0 || pos >= int(hb.ops.size()) || e_alpha < 0 || e_alpha > ma || e_beta < 0 || e_beta > mb || which < 0 || which > 2)
+        return fail(TCC_ERR_BAD_ARGUMENT, "bad excitation position, electron count or list kind");
+    const size_t slot = ((size_t(pos) * (ma + 1) + e_alpha) * (mb + 1) + e_beta) * 2;
+    const uint32_t* src = nullptr;
+    int64_t n = 0;
+    if (round_len) *round_len = 0;
+    if (which == 0) {
+        if (slot + 1 >= hb.plist_index.size()) return fail(TCC_ERR_BAD_ARGUMENT, "no pair list");
+        src = hb.plist.data() + hb.plist_index[slot];
+        n = hb.plist_index[slot + 1];
+    } else {
+        if (!hb.lean_threads || slot + 1 >= hb.stream_index.size()) {
+            *n_out = 0;  // a batch without lean streams (a side without active orbitals)
+            return 0;
+        }
+        int ga = 1, gb = 1;
+        for (const PanelDesc& pd : hb.A.panels)
+            if (int(pd.e) == e_alpha) ga = std::max<int>(1, pd.Gn);
+        for (const PanelDesc& pd : hb.B.panels)
+            if (int(pd.e) == e_beta) gb = std::max<int>(1, pd.Gn);
+        const int tps = std::max(1, hb.lean_threads / (ga * gb));
+        src = (which == 1 ? hb.stream8.data() : hb.stream16.data()) + hb.stream_index[slot];
+        n = int64_t(hb.stream_index[slot + 1]) * tps;
+        if (round_len) *round_len = tps;
+    }
+    *n_out = int32_t(n);
+    if (out_host) {
+        if (capacity < n) return fail(TCC_ERR_BAD_ARGUMENT, "output buffer too small");
+        for (int64_t i = 0; i < n; ++i) out_host[i] = src[i];
+    }
+    return 0;
+}
+
 int tcc_ci_strings_spin(const tcc_plan* p, uint64_t* out_host) {
     if (!p || !out_host) return fail(TCC_ERR_BAD_ARGUMENT, "null argument");
     for (int64_t r = 0; r < p->hp.nstr; ++r) out_host[r] = p->hp.strings[p->hp.ref2int[r]];

@@ -109,6 +109,18 @@ class Plan:
         info["op_indices"] = idx[:n_ops].tolist()
         return info
 
+    def batch_pairs(self, b: int, pos: int, e_alpha: int, e_beta: int, which: int = 0, with_round_len: bool = False):
+        """Pair list (which=0) or lean stream (1: 8-byte, 2: 16-byte elements) of one excitation of a batch for tiles
+        of class pair (e_alpha, e_beta), as uint32 entries (include/tcc_b200.h, tcc_batch_pairs); optionally also the
+        number of entries per round of a stream."""
+        n, rl = C.c_int32(0), C.c_int32(0)
+        _lib.check(self.lib.tcc_batch_pairs(self.handle, int(b), int(pos), int(e_alpha), int(e_beta), int(which), None, 0,
+                                            C.byref(n), C.byref(rl)))
+        out = np.zeros(max(n.value, 1), dtype=np.uint32)
+        _lib.check(self.lib.tcc_batch_pairs(self.handle, int(b), int(pos), int(e_alpha), int(e_beta), int(which),
+                                            out.ctypes.data_as(C.POINTER(C.c_uint32)), int(out.size), C.byref(n), C.byref(rl)))
+        return (out[: n.value], rl.value) if with_round_len else out[: n.value]
+
     # ---- alpha-row sharding (include/tcc_b200.h, multi-GPU section) ----
     def shard_info(self) -> dict:
         v = [C.c_int32(0) for _ in range(4)]

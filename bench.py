@@ -202,6 +202,27 @@ def workload_config(n, args):
             "n_params": len(set(pids))}
 
 
+CONFIG_KEYS = ("workload", "n_determinants", "n_excitations", "n_params", "l2")
+
+
+def l2_note(size, world=1, sharded=False):
+    """how the timed region keeps L2 from serving the vectors (both arms print the same note for the same workload)"""
+    if sharded and world > 1:
+        return "inputs larger than L2 (ket + bra shards vs 126 MB)" if 2 * size * 8 / world > 1.26e8 else "vectors fit in L2; no flush"
+    return "inputs larger than L2 (1.3 GB vectors vs 126 MB)" if size * 8 > 2.5e8 else "vectors fit in L2; no flush"
+
+
+def emit(line):
+    """print the JSON line; `config` keeps the workload keys both arms share (CONFIG_KEYS), everything else that
+    describes how THIS engine ran the workload (sharding, batches, staging time) goes to `engine_config`"""
+    cfg = line.get("config", {})
+    extra = {k: v for k, v in cfg.items() if k not in CONFIG_KEYS}
+    line["config"] = {k: cfg[k] for k in CONFIG_KEYS if k in cfg}
+    if extra:
+        line["engine_config"] = extra
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     """`--impl reference`: the CPU port of the reference's numpy engine on this box's host cores, rank 0 only.  One
     full evaluation takes hours at (16e,16o), so a step is a bounded sample extrapolated by operation counts
@@ -215,6 +236,7 @@ def run_reference(args):
     res = cpu_reference_sample(n, n_ops_sample=2, ansatz=args.ansatz)
     t_eval = 1.0 / res["value"]
     cfg = workload_config(n, args)
+    cfg["l2"] = l2_note(cfg["n_determinants"], args.gpus, args.multi == "sharded" and args.batch == 0 and args.ansatz != "puccd")
     cfg["note"] = ("CPU oracle port of the reference numpy engine; the bounded sample is timed once and extrapolated by "
                    "operation counts to one evaluation; every step reports that figure")
     line = {
@@ -227,7 +249,7 @@ def run_reference(args):
         "e2e": {"value": 1.0 / t_eval, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def progress(msg):
@@ -413,7 +435,7 @@ def run_b200(args):
         "scaling": "weak" if world > 1 else scaling_label(args, world), "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_desc(n, args.ansatz, args.integrals), "n_determinants": size, "n_excitations": m, "n_params": p_count,
-                   "l2": "inputs larger than L2 (1.3 GB vectors vs 126 MB)" if size * 8 > 2.5e8 else "vectors fit in L2; no flush",
+                   "l2": l2_note(size),
                    "multi_gpu": "independent theta sets per rank, no data-path collective" if world > 1 else "single GPU",
                    "n_batches": plan.n_batches, "staging_s": round(staging_s, 2)},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": 8 * p_count, "d2h_bytes_per_step": 8 * (m + 1),
@@ -436,7 +458,7 @@ def run_b200(args):
             line["cpu_baseline"] = cpu_reference_sample(n, n_ops_sample=2, ansatz=args.ansatz)
         except Exception as exc:  # pragma: no cover
             line["cpu_baseline"] = {"error": repr(exc)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -529,7 +551,7 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_desc(n, args.ansatz, args.integrals) + (f" TRUNCATED to the first {m} excitations" if args.max_ops > 0 else ""),
                    "n_determinants": size, "n_excitations": m,
-                   "n_params": p_count, "l2": "inputs larger than L2 (ket + bra shards vs 126 MB)" if 2 * size * 8 / world > 1.26e8 else "vectors fit in L2; no flush",
+                   "n_params": p_count, "l2": l2_note(size, world, True),
                    "multi_gpu": f"one evaluation, CI vector sharded by alpha rows over {world} ranks; {reshards} row re-shards "
                                 + ("(rows written straight into the peers' shard pool over NVLink, tcc_push_rows) " if getattr(eng.pool, "p2p", False)
                                    else "(pack, NCCL all-to-all, unpack) ")
@@ -559,7 +581,7 @@ def run_b200_sharded(args, ucc, int1e, int2e, world, rank, local_rank, n):
         line["parity"] = parity
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = {"note": "reported by the N=1 run (rank 0, bounded sample); not repeated at N>1"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     dist.destroy_process_group()
 
 
@@ -627,7 +649,7 @@ def run_b200_batched(args, plan, ucc, theta, barrier, world, rank, n, staging_s)
             line["cpu_baseline"] = cpu_reference_sample(n, n_ops_sample=2, ansatz=args.ansatz)
         except Exception as exc:  # pragma: no cover
             line["cpu_baseline"] = {"error": repr(exc)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

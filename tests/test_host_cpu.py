@@ -282,3 +282,22 @@ def test_pair_lists_and_streams_hold_the_same_rotations(n, tile_elems, monkeypat
     assert clash_ordered <= clash_plain
     if n == 8:
         assert clash_ordered < 0.5 * clash_plain  # the matching removes most clashes of the unordered streams
+
+
+def test_bench_arms_share_the_config_keys(capsys):
+    """Both bench arms print `config` with the same workload keys (the driver compares them); what only describes how
+    this engine ran the workload (sharding, batches, staging) moves to `engine_config`."""
+    import importlib.util
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    line = {"metric": bench.METRIC, "config": {"workload": "w", "n_determinants": 36, "n_excitations": 26, "n_params": 15,
+                                               "l2": bench.l2_note(36), "multi_gpu": "single GPU", "n_batches": 3, "staging_s": 0.1}}
+    bench.emit(line)
+    d = json.loads(capsys.readouterr().out)
+    assert tuple(d["config"]) == bench.CONFIG_KEYS
+    assert d["engine_config"] == {"multi_gpu": "single GPU", "n_batches": 3, "staging_s": 0.1}
+    assert bench.l2_note(165636900) == bench.l2_note(165636900, 1, True) != bench.l2_note(165636900, 8, True)

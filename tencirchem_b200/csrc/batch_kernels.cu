@@ -1152,12 +1152,12 @@ static void fan_out(const std::vector<TileRect>& rects, cudaStream_t st, StreamF
 
 // v_out: null = in place (static column order); otherwise out of place with the dynamic column layout (BatchDev::B.dyn_*)
 void launch_batch_forward(double* v, double* v_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan, unsigned* ctl, int sms) {
+                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan, unsigned* ctl, int sms, int min_waves) {
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         dim3 grid(unsigned(r.pa_cnt) * unsigned(r.pb_cnt), unsigned(n_sets), 1);
         if (grid.x == 0) return;  // a rank of a sharded plan may own no class of this batch
         const size_t ri = size_t(&r - rects.data());
-        if (bd.lean && ctl && !v_out && n_sets == 1 && r.ctas_p_fwd > 0 && ri < 16) {
+        if (bd.lean && ctl && !v_out && n_sets == 1 && r.ctas_p_fwd > 0 && ri < 16 && grid.x >= unsigned(min_waves) * unsigned(r.ctas_p_fwd) * unsigned(sms)) {
             const unsigned ctas = std::min(grid.x, unsigned(r.ctas_p_fwd) * unsigned(sms));
             lean_persist_kernel<1><<<ctas, threads, r.smem_p_fwd, s>>>(v, nb, bd, rot, nullptr, 0, r, ctl + 2 * ri, r.max_rows, r.max_cols);
             return;
@@ -1189,13 +1189,15 @@ void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& 
 // order of the next batch of the sweep (BatchDev::B.dyn_*, dynamic column layout)
 void launch_batch_reverse_il(double* kb, double* kb_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
                              int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan,
-                             unsigned* ctl, int sms) {
+                             unsigned* ctl, int sms, int min_waves) {
     const int n_tiles = bd.B.n_panels * bd.A.n_panels;
     fan_out(rects, st, fan, [&](const TileRect& r, cudaStream_t s) {
         const unsigned tiles = unsigned(r.pa_cnt) * unsigned(r.pb_cnt);
         if (tiles == 0) return;
         const size_t ri = size_t(&r - rects.data());
-        if (ctl && !kb_out && n_sets == 1 && r.ctas_p_rev > 0 && ri < 16) {
+        // persistent kernel only when every resident CTA gets several tiles: with about as many tiles as CTAs the ticket
+        // look-ahead (two tickets per CTA at start) would leave half the SMs idle -- (12e,12o): 2.46 vs 1.37 ms per sweep
+        if (ctl && !kb_out && n_sets == 1 && r.ctas_p_rev > 0 && ri < 16 && tiles >= unsigned(min_waves) * unsigned(r.ctas_p_rev) * unsigned(sms)) {
             const unsigned ctas = std::min(tiles, unsigned(r.ctas_p_rev) * unsigned(sms));
             lean_persist_kernel<3><<<ctas, threads, r.smem_p_rev, s>>>(kb, nb, bd, rot, partials, n_tiles, r, ctl + 32 + 2 * ri, r.max_rows, r.max_cols);
             return;

@@ -77,11 +77,11 @@ size_t lean_persist_smem_bytes(int max_rows, int max_cols, int nops, int nv);
 void persist_config(int nv, int threads, int max_rows, int max_cols, int nops, size_t* smem, int* ctas_per_sm);
 void launch_batch_reverse_il(double* kb, double* kb_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
                              int threads, double* partials, double* grad_ops, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan,
-                             unsigned* ctl = nullptr, int sms = 148);
+                             unsigned* ctl = nullptr, int sms = 148, int min_waves = 4);
 void launch_interleave(const double* a, const double* b, double* out, int64_t n, cudaStream_t st);
 void launch_deinterleave(const double* in, double* a, double* b, int64_t n, cudaStream_t st);
 void launch_batch_forward(double* v, double* v_out, int64_t nb, const BatchDev& bd, const double2* rot, const std::vector<TileRect>& rects,
-                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan, unsigned* ctl = nullptr, int sms = 148);
+                          int threads, int n_sets, SetStrides ss, cudaStream_t st, StreamFan* fan, unsigned* ctl = nullptr, int sms = 148, int min_waves = 4);
 void launch_batch_reverse(double* ket, double* bra, int64_t nb, const BatchDev& bd, const double2* rot,
                           const std::vector<TileRect>& rects, int threads, double* partials, double* grad_ops, int n_sets,
                           SetStrides ss, cudaStream_t st, StreamFan* fan);

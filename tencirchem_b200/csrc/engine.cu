@@ -145,7 +145,9 @@ struct tcc_plan {
     int lean = 1;           // lean per-thread streams for two-sided batches (TCC_B200_LEAN=0: the plain pair lists)
     int lean_fwd = 0;       // forward sweep on the lean kernel too (TCC_B200_LEAN_FWD=1); measured slower than batch_kernel<1>
     int rev_interleave = 1; // reverse sweep on interleaved (ket, bra) elements (TCC_B200_REV_IL=0: two vectors)
-    int persist_rev = 1;    // reverse sweep on the persistent kernel (lean_persist_kernel<3>; TCC_B200_PERSIST=0: one tile per CTA)
+    int persist_rev = 1;    // reverse sweep on the persistent kernel (lean_persist_kernel<3>; TCC_B200_PERSIST=0: one tile per CTA,
+                            // =2: also for launches with few tiles -- the default uses it from 4 tiles per resident CTA on)
+    int persist_min_waves = 4;
     int persist_fwd = 0;    // forward sweep on lean_persist_kernel<1> (TCC_B200_PERSIST_FWD=1; needs the lean forward streams)
     unsigned* persist_ctl = nullptr;  // ticket counters of the persistent launches [2][16][2], self-resetting
     int sms = 148;
@@ -469,6 +471,7 @@ static int plan_create_impl(int n_qubits, int n_elec, int hcb, int n_ops, const 
               p->batch_threads >= 64;
     p->rev_interleave = p->lean && env_int("TCC_B200_REV_IL", 1) != 0;
     p->persist_rev = env_int("TCC_B200_PERSIST", 1) != 0;
+    p->persist_min_waves = env_int("TCC_B200_PERSIST", 1) == 2 ? 0 : 4;
     p->persist_fwd = p->lean && env_int("TCC_B200_PERSIST_FWD", 0) != 0;
     p->lean_fwd = p->lean && (env_int("TCC_B200_LEAN_FWD", 0) != 0 || p->persist_fwd);
     p->hp.error.clear();
@@ -923,7 +926,7 @@ static int forward_sweep(tcc_plan* p, const double* params, double* vec, cudaStr
             BatchDevSet& db = p->dbatches[b];
             if (p->btimer.on) cudaEventRecord(p->btimer.ev[b], st);
             launch_batch_forward(cur, other, hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st, &p->fan,
-                                 p->persist_ctl, p->sms);
+                                 p->persist_ctl, p->sms, p->persist_min_waves);
             if (other) std::swap(cur, other);
             p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * hp.N);
             p->launches += 1;
@@ -993,7 +996,7 @@ static int reverse_sweep(tcc_plan* p, const double* params, double* ket, double*
                     in_kb = true;
                 }
                 launch_batch_reverse_il(kb_cur, kb_other, hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart,
-                                        p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan, p->persist_ctl, p->sms);
+                                        p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan, p->persist_ctl, p->sms, p->persist_min_waves);
                 if (kb_other) std::swap(kb_cur, kb_other);
             } else {
                 if (in_kb) {
@@ -1491,7 +1494,7 @@ int tcc_shard_forward(tcc_plan* p, int seg, double* vec_local_dev, void* stream)
     for (int b = s.batch_lo; b < s.batch_hi; ++b) {
         BatchDevSet& db = p->dbatches[b];
         launch_batch_forward(vec_local_dev, nullptr, p->hp.nb, db.fwd, p->d_rot_fwd, db.rects, p->batch_threads, 1, SetStrides{0, 0, 0, 0}, st,
-                             &p->fan, p->persist_ctl, p->sms);
+                             &p->fan, p->persist_ctl, p->sms, p->persist_min_waves);
         p->prof.count(TCC_PROF_FWD_BATCH, 1, 16 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
         p->launches += 1;
     }
@@ -1537,7 +1540,7 @@ int tcc_shard_reverse_interleaved(tcc_plan* p, int seg, double* kb_local_dev, vo
     for (int b = s.batch_hi - 1; b >= s.batch_lo; --b) {
         BatchDevSet& db = p->dbatches[b];
         launch_batch_reverse_il(kb_local_dev, nullptr, p->hp.nb, db.rev, p->d_rot_rev, db.rects_rev, p->batch_threads_rev, p->bpart,
-                                p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan, p->persist_ctl, p->sms);
+                                p->grad_ops, 1, SetStrides{0, 0, 0, 0}, st, &p->fan, p->persist_ctl, p->sms, p->persist_min_waves);
         p->prof.count(TCC_PROF_REV_BATCH, 1, 32 * int64_t(p->hp.layouts[s.layout].rows[p->hp.shard_rank]) * p->hp.nb);
         p->launches += 2;
     }

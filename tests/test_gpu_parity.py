@@ -306,12 +306,13 @@ def test_small_tiles_many_batches(tile_elems, threads, monkeypatch):
     clear_cache()
 
 
-@pytest.mark.parametrize("persist,persist_fwd,sched", [("1", "1", "2"), ("0", "0", "0"), ("1", "0", "1")])
+@pytest.mark.parametrize("persist,persist_fwd,sched", [("2", "1", "2"), ("0", "0", "0"), ("2", "0", "1"), ("1", "0", "0")])
 @pytest.mark.parametrize("tile_elems", [64, 400, 6144])
 def test_persistent_kernels_and_schedulers_against_oracle(tile_elems, persist, persist_fwd, sched, monkeypatch):
     """The persistent batch kernel (lean_persist_kernel: ticketed tiles, next tile resolved during the gather) in the
     reverse sweep (default) AND in the forward sweep (TCC_B200_PERSIST_FWD=1), the classic one-tile-per-CTA kernels
-    (TCC_B200_PERSIST=0), and the three batch schedulers (TCC_B200_SCHED), from a handful to thousands of tiles per
+    (TCC_B200_PERSIST=0; =2 forces the persistent kernel also for launches with few tiles, =1 is the default: from
+    four tiles per resident CTA on), and the three batch schedulers (TCC_B200_SCHED), from a handful to thousands of tiles per
     launch (more tiles than resident CTAs, so every CTA takes several tickets): state, energy, gradient, with an
     init_state, twice in a row (the ticket counters reset themselves between launches)."""
     monkeypatch.setenv("TCC_B200_TILE_ELEMS", str(tile_elems))
